@@ -1,0 +1,166 @@
+"""CPU tests: the oracle against the committed golden vectors and against independent known answers."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sd3_oracle as O
+
+
+def _checksum(ts):
+    return torch.stack([t.double().abs().sum() for t in ts])
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg = O.tiny_config()
+    pipe = O.build_pipeline(cfg)
+    inp = O.synthetic_inputs(cfg, batch=2)
+    return cfg, pipe, inp
+
+
+def test_seeded_weights_and_inputs_reproduce(tiny, golden):
+    _, pipe, inp = tiny
+    fx = golden("tiny_traj")
+    assert torch.allclose(_checksum(pipe.state_dict().values()), fx["weights_checksum"], rtol=1e-12)
+    assert torch.allclose(_checksum(inp.values()), fx["inputs_checksum"], rtol=1e-12)
+
+
+def test_tiny_trajectory_matches_golden(tiny, golden):
+    _, pipe, inp = tiny
+    fx = golden("tiny_traj")
+    out = pipe(**inp, max_inference_steps=8, predict=True, record_velocity=True)
+    assert torch.allclose(out["sigmas"], fx["sigmas"], atol=1e-6)
+    assert torch.allclose(out["alphas"], fx["alphas"], rtol=1e-5)
+    assert torch.allclose(out["logprobs"], fx["logprobs"], atol=1e-5)
+    assert torch.equal(out["prob_masks"].to(torch.uint8), fx["prob_masks"])
+    rel = (out["velocities"] - fx["velocities"]).norm() / fx["velocities"].norm()
+    assert rel < 1e-5
+    assert (out["final_latents"] - fx["final_latents"]).norm() / fx["final_latents"].norm() < 1e-5
+
+
+def test_injected_ratio_trajectory(tiny, golden):
+    _, pipe, inp = tiny
+    fx = golden("tiny_traj")
+    out = pipe(**inp, max_inference_steps=8, predict=False, ratios=fx["sample.ratios"])
+    assert torch.allclose(out["sigmas"], fx["sample.sigmas"], atol=1e-6)
+    assert torch.allclose(out["sigmas"][:, 0], fx["sample.ratios"][:, 0])
+    assert torch.allclose(out["logprobs"], fx["sample.logprobs"], atol=1e-5)
+
+
+def test_tpm_matches_reference_fixture(golden):
+    fx = golden("tpm_ref")
+    tpm = O.OracleTimePredictor(128, 128)
+    tpm.load_state_dict({k: v for k, v in fx.items() if not k.startswith("grad.") and k not in ("x", "temb", "alpha_beta")})
+    y = tpm(fx["x"], fx["temb"])
+    assert torch.equal(y, fx["alpha_beta"])
+    y.log().sum().backward()
+    for k, p in tpm.named_parameters():
+        assert torch.allclose(p.grad, fx["grad." + k], rtol=1e-5, atol=1e-7), k
+
+
+def test_pieces_match_reference_fixture(golden):
+    fx = golden("pieces_ref")
+    assert torch.equal(O.custom_step(fx["euler.model_output"], fx["euler.sigma_next"], fx["euler.sigma"], fx["euler.sample"]),
+                       fx["euler.prev"])
+    a, b = O.get_ref_beta(fx["refbeta.sigma"])
+    assert torch.equal(a, fx["refbeta.alpha"]) and torch.equal(b, fx["refbeta.beta"])
+    # reference_distributions: sigma=1 -> (18.758, 1.242)
+    a1, b1 = O.get_ref_beta(torch.tensor([1.0]))
+    assert abs(float(a1) - 18.758) < 2e-3 and abs(float(b1) - 1.242) < 2e-3
+    # closed-form KL == torch.distributions (train_utilis.py:36-45 known-answer block)
+    kl = O.get_kl_beta(torch.tensor(2.0), torch.tensor(5.0), torch.tensor(3.0), torch.tensor(4.0))
+    assert torch.equal(kl.reshape(1), fx["kl_2_5_3_4"])
+    ref = torch.distributions.kl_divergence(torch.distributions.Beta(torch.tensor(5.0), torch.tensor(2.0)),
+                                            torch.distributions.Beta(torch.tensor(4.0), torch.tensor(3.0)))
+    assert abs(float(kl) - float(ref)) < 1e-5
+
+
+def test_scramble_formula(golden):
+    """token n -> pixel (2*(n//(2g)) + (n%4)//2, 2*((n%(2g))//4) + n%2): the closed form the CUDA relayout uses."""
+    fx = golden("pieces_ref")
+    g = 8
+    want = fx["scramble8"]
+    got = torch.empty(g, g)
+    for n in range(g * g):
+        y = 2 * (n // (2 * g)) + (n % 4) // 2
+        x = 2 * ((n % (2 * g)) // 4) + n % 2
+        got[y, x] = n
+    assert torch.equal(got, want)
+
+
+def test_beta_log_prob_matches_torch():
+    a, b, x = torch.tensor(5.7), torch.tensor(2.7), torch.tensor(0.74)
+    assert abs(float(O.beta_log_prob(a, b, x)) - float(torch.distributions.Beta(a, b).log_prob(x))) < 1e-5
+
+
+def test_sincos_matches_mae_reference():
+    """Cross-check against the MAE sincos code that transformers ships (same published algorithm)."""
+    mae = pytest.importorskip("transformers.models.vit_mae.modeling_vit_mae")
+    ours = O.get_2d_sincos_pos_embed(64, 12, base_size=12)   # scale factor 1 -> plain MAE table
+    theirs = mae.get_2d_sincos_pos_embed(64, 12, add_cls_token=False)
+    assert np.allclose(ours, theirs, atol=1e-6)
+    # coordinate scaling: pos_embed_max_size 96 with base 16 -> coordinate i/6
+    t = O.get_2d_sincos_pos_embed(16, 96, base_size=16)
+    assert abs(t[6, 0] - math.sin(1.0)) < 1e-6          # column coordinate of grid index (0,6) is 1.0 -> first channel sin(1*w0)
+    assert abs(t[96 * 6, 8] - math.sin(1.0)) < 1e-6     # row coordinate lives in the second half
+
+
+def test_timestep_embedding_layout():
+    e = O.get_timestep_embedding(torch.tensor([500.0]))
+    assert e.shape == (1, 256)
+    assert abs(float(e[0, 0]) - math.cos(500.0)) < 1e-4 and abs(float(e[0, 128]) - math.sin(500.0)) < 1e-4
+
+
+def test_block_golden(tiny, golden):
+    _, pipe, inp = tiny
+    fx = golden("tiny_block")
+    lat2 = torch.cat([inp["latents"]] * 2)
+    pe = torch.cat([inp["negative_prompt_embeds"], inp["prompt_embeds"]])
+    pp = torch.cat([inp["negative_pooled_prompt_embeds"], inp["pooled_prompt_embeds"]])
+    with torch.no_grad():
+        v, temb, h1, h2, blocks = pipe.transformer(lat2, pe, pp, fx["timestep"], return_blocks=True)
+    assert torch.allclose(v, fx["velocity"], atol=1e-5)
+    assert torch.allclose(temb, fx["temb"], atol=1e-5)
+    assert torch.allclose(blocks[1][:, 5], fx["block1_tok5"], atol=1e-5)
+    # CFG halves of h1 are identical when the two latents are
+    assert torch.equal(h1[0], h1[2])
+
+
+def test_joint_attention_is_image_first_unmasked_softmax():
+    torch.manual_seed(0)
+    att = O.JointAttention(32, 2, 16, context_pre_only=False, qk_norm="rms_norm")
+    x, c = torch.randn(1, 5, 32), torch.randn(1, 3, 32)
+    o_img, o_ctx = att(x, c)
+    # hand computation
+    def heads(t):
+        return t.view(1, -1, 2, 16).transpose(1, 2)
+    q = torch.cat([att.norm_q(heads(att.to_q(x))), att.norm_added_q(heads(att.add_q_proj(c)))], 2)
+    k = torch.cat([att.norm_k(heads(att.to_k(x))), att.norm_added_k(heads(att.add_k_proj(c)))], 2)
+    v = torch.cat([heads(att.to_v(x)), heads(att.add_v_proj(c))], 2)
+    p = torch.softmax(q @ k.transpose(-1, -2) / 4.0, -1)
+    o = (p @ v).transpose(1, 2).reshape(1, 8, 32)
+    assert torch.allclose(o_img, att.to_out[0](o[:, :5]), atol=1e-5)
+    assert torch.allclose(o_ctx, att.to_add_out(o[:, 5:]), atol=1e-5)
+
+
+def test_rloo_pieces():
+    r = torch.tensor([1.0, 2.0, 3.0, 5.0])          # k=2 repeats x 2 prompts: [[1,2],[3,5]]
+    adv = O.rloo_advantage(r, 2)
+    assert torch.allclose(adv, torch.tensor([-2.0, -3.0, 2.0, 3.0]))
+    new, old = torch.tensor([[0.1, 0.2]]), torch.tensor([[0.0, 0.0]])
+    loss = O.ppo_clip_loss(new, old, torch.tensor([1.0]), 0.2)
+    assert abs(float(loss) + 1.2) < 1e-6             # ratio e^0.3=1.35 clipped at 1.2, A>0 -> max(-1.35,-1.2)
+    assert abs(O.discounted_reward(2.0, 2, 0.5) - 2.0 * (0.25 + 0.5 + 1) / 3) < 1e-9
+
+
+def test_only_predict_logprobs_replays_sampling(tiny):
+    _, pipe, inp = tiny
+    g = torch.Generator().manual_seed(5)
+    ratios = torch.rand(2, 4, generator=g) * 0.6 + 0.2
+    out = pipe(**inp, max_inference_steps=4, predict=False, ratios=ratios)
+    lp = pipe.only_predict_logprobs(out["sigmas"], out["hidden_states_combineds"], out["tembs"])["logprobs"]
+    assert torch.allclose(lp, out["logprobs"], atol=1e-4)
+    with pytest.raises(ValueError):
+        pipe.only_predict_logprobs(None, None, None)

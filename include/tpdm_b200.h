@@ -1,0 +1,194 @@
+/* tpdm_b200.h -- C ABI of libtpdm_b200.so: the TPDM adaptive denoising hot path on B200 (sm_100a).
+ *
+ * The reference (jinkyu032/TPDM) is pure Python and has no FFI; its boundary for this path is the Python call surface
+ * (SURVEY.md section 8b).  The Python classes in tpdm_b200/ keep that surface and bind the entry points below with
+ * ctypes; each entry point names the reference code it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - every call returns int: 0 = ok, <0 = tpdm_status; the message is in tpdm_last_error() (thread-local);
+ *   - no C++ exception crosses the boundary; there is NO CPU fallback: without a CUDA device every compute call fails;
+ *   - all tensor arguments are DEVICE pointers, fp32 unless stated, contiguous, borrowed for the duration of the call
+ *     and ordered on the cudaStream_t passed as `void* stream` (0 = legacy default stream);
+ *   - weights are borrowed for the lifetime of the ctx (the caller keeps them alive; packing is described per field);
+ *   - no allocation on the hot path: the caller supplies the workspace a plan is bound to;
+ *   - a ctx / plan is bound to the current CUDA device at creation and is not thread-safe.
+ */
+#ifndef TPDM_B200_H_
+#define TPDM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPDM_ABI_VERSION 1
+
+typedef enum tpdm_status {
+  TPDM_OK = 0,
+  TPDM_ERR_ARG = -1,    /* null / inconsistent argument  -> Python raises ValueError   */
+  TPDM_ERR_SHAPE = -2,  /* unsupported shape             -> ValueError                 */
+  TPDM_ERR_CUDA = -3,   /* CUDA runtime / driver failure -> RuntimeError               */
+  TPDM_ERR_STATE = -4,  /* call order (weights not set, plan not begun ...) -> RuntimeError */
+  TPDM_ERR_NOMEM = -5   /* workspace too small           -> RuntimeError               */
+} tpdm_status;
+
+/* Mirrors CustomSD3Transformer2DModel.__init__ (src/models/stable_diffusion_3/transformer_sd3.py:91-108) plus the
+ * TimePredictor / pipeline knobs (src/models/stable_diffusion_3/modeling_sd3_pnt.py:86,129-140,195-198). */
+typedef struct tpdm_config {
+  int32_t num_layers;
+  int32_t num_heads;
+  int32_t head_dim;
+  int32_t joint_attention_dim; /* 4096 */
+  int32_t pooled_projection_dim; /* 2048 */
+  int32_t in_channels;  /* 16 */
+  int32_t out_channels; /* 16 */
+  int32_t patch_size;   /* 2 (only 2 is supported) */
+  int32_t pos_embed_max_size;
+  int32_t qk_norm;      /* 0 = None, 1 = "rms_norm" */
+  int32_t tpm_channels; /* TimePredictor conv_out_channels, 128 */
+  int32_t prediction_type; /* 0 = "alpha_beta", 1 = "mode_concentration" */
+  int32_t relative;     /* 1 = sigma_next = sigma * ratio, 0 = sigma - ratio */
+  float min_sigma;
+  float epsilon;        /* ratio clamp, 1e-3 (modeling_sd3_pnt.py:197) */
+  float tpm_epsilon;    /* exp(x) + 1.0 (modeling_sd3_pnt.py:95,115) */
+} tpdm_config;
+
+/* Per JointTransformerBlock weights (diffusers state-dict names in comments; D = num_heads*head_dim, dp = head_dim
+ * rounded up to 64 or 128, Dp = num_heads*dp).  bf16 matrices are row-major [out][in] exactly as nn.Linear stores them. */
+typedef struct tpdm_block_weights {
+  const void* qkv_w;    /* bf16 [3*Dp][D]  rows: attn.to_q | to_k | to_v, each head padded to dp rows (zeros) */
+  const float* qkv_b;   /* [3*Dp] */
+  const void* cqkv_w;   /* bf16 [3*Dp][D]  attn.add_q_proj | add_k_proj | add_v_proj */
+  const float* cqkv_b;
+  const void* out_w;    /* bf16 [D][Dp]    attn.to_out.0 (columns of padded head dims are zero) */
+  const float* out_b;
+  const void* cout_w;   /* bf16 [D][Dp]    attn.to_add_out            (null in the last block) */
+  const float* cout_b;
+  const void* ff1_w;    /* bf16 [4D][D]    ff.net.0.proj */
+  const float* ff1_b;
+  const void* ff2_w;    /* bf16 [D][4D]    ff.net.2 */
+  const float* ff2_b;
+  const void* cff1_w;   /* ff_context.net.0.proj (null in the last block) */
+  const float* cff1_b;
+  const void* cff2_w;   /* ff_context.net.2 */
+  const float* cff2_b;
+  const float* norm_q;  /* [dp] attn.norm_q.weight (zero padded), null when qk_norm == 0 */
+  const float* norm_k;
+  const float* norm_added_q;
+  const float* norm_added_k;
+} tpdm_block_weights;
+
+typedef struct tpdm_weights {
+  const float* patch_w;   /* [D][in_channels*4]  pos_embed.proj.weight flattened (c, p, q) */
+  const float* patch_b;   /* [D] */
+  const float* pos_table; /* [pos_embed_max_size^2][D]  pos_embed.pos_embed */
+  const float* t_w1;      /* [D][256]   time_text_embed.timestep_embedder.linear_1 */
+  const float* t_b1;
+  const float* t_w2;      /* [D][D]     ...linear_2 */
+  const float* t_b2;
+  const float* p_w1;      /* [D][pooled] time_text_embed.text_embedder.linear_1 */
+  const float* p_b1;
+  const float* p_w2;      /* [D][D] */
+  const float* p_b2;
+  const void* ctx_w;      /* bf16 [D][joint_attention_dim]  context_embedder */
+  const float* ctx_b;
+  const void* adaln_w;    /* bf16 [R][D], R = 12*D*L - 2*D: for block i rows [12Di, 12Di+6D) = norm1.linear,
+                             [12Di+6D, ..) = norm1_context.linear (6D rows; last block 2D rows), then norm_out.linear (2D) */
+  const float* adaln_b;   /* [R] */
+  const void* proj_w;     /* bf16 [4*out_channels][D]  proj_out */
+  const float* proj_b;
+  const tpdm_block_weights* blocks; /* HOST array [num_layers] */
+  /* TimePredictor (modeling_sd3_pnt.py:85-126) */
+  const void* tpm_conv1_w;    /* bf16 [C1][9][2D]  conv1.weight permuted (oc, ky*3+kx, c) */
+  const float* tpm_conv1_b;   /* [C1] */
+  const float* tpm_lin_w;     /* [2*C1][D]  norm1.linear */
+  const float* tpm_lin_b;
+  const float* tpm_gn_w;      /* [C1] norm1.norm.weight */
+  const float* tpm_gn_b;
+  const float* tpm_conv2_w;   /* [9][C1 in][C1 out]  conv2.weight permuted (ky*3+kx, c, oc) */
+  const float* tpm_conv2_b;
+  const float* tpm_fc1_w;     /* [128][C1] */
+  const float* tpm_fc1_b;
+  const float* tpm_fc2_w;     /* [2][128] */
+  const float* tpm_fc2_b;
+} tpdm_weights;
+
+typedef struct tpdm_ctx tpdm_ctx;
+typedef struct tpdm_plan tpdm_plan;
+
+const char* tpdm_last_error(void);
+int tpdm_abi_version(void);
+
+int tpdm_create(const tpdm_config* cfg, tpdm_ctx** out);
+int tpdm_destroy(tpdm_ctx* ctx);
+/* Borrow the packed weights (copied struct, borrowed pointers).  Replaces module construction / load_state_dict
+ * (modeling_sd3_pnt.py:144-157, gradio_sd3_inference.py:20-21). */
+int tpdm_set_weights(tpdm_ctx* ctx, const tpdm_weights* w);
+
+/* A plan fixes the shapes: `batch` prompts (transformer batch Bt = 2*batch when cfg_pairs != 0, i.e. the loop's
+ * cat([latents]*2) at modeling_sd3_pnt.py:524; else Bt = batch), latent side, text tokens, recorded steps. */
+size_t tpdm_plan_workspace_bytes(const tpdm_ctx* ctx, int batch, int cfg_pairs, int latent_h, int latent_w, int n_text,
+                                 int max_steps);
+int tpdm_plan_create(tpdm_ctx* ctx, int batch, int cfg_pairs, int latent_h, int latent_w, int n_text, int max_steps,
+                     void* workspace, size_t workspace_bytes, tpdm_plan** out);
+int tpdm_plan_destroy(tpdm_plan* plan);
+
+/* CustomSD3Transformer2DModel.forward (transformer_sd3.py:299-409).  Bt rows everywhere.
+ *   latents [Bt][C][h][w], timestep [Bt], enc [Bt][T][joint_attention_dim], pooled [Bt][pooled_projection_dim]
+ *   -> out_sample [Bt][C][h][w], out_temb [Bt][D], out_h1 [Bt][N][D], out_h2 [Bt][N][D]   (any out may be null) */
+int tpdm_mmdit_forward(tpdm_plan* plan, const float* latents, const float* timestep, const float* enc,
+                       const float* pooled, float* out_sample, float* out_temb, float* out_h1, float* out_h2,
+                       void* stream);
+
+/* TimePredictor.forward (modeling_sd3_pnt.py:100-115) on NCHW input x [batch][2D][g][g], temb [batch][D] -> [batch][2]. */
+int tpdm_tpm_forward(tpdm_plan* plan, const float* x_nchw, const float* temb, float* out_alpha_beta, void* stream);
+
+/* CustomFlowMatchEulerDiscreteScheduler.custom_step (src/models/model_utilis.py:52-74):
+ *   prev = sample + (sigma_next - sigma)[:,None,None,None] * model_output   (fp32; n = elements per sample) */
+int tpdm_euler_step(const float* model_output, const float* sigma_next, const float* sigma, const float* sample,
+                    float* prev_sample, int batch, long long n, void* stream);
+
+/* The adaptive loop, SD3PredictNextTimeStepModel.forward (modeling_sd3_pnt.py:504-612).
+ * begin: latents [batch][C][h][w]; embeddings for the negative and positive prompt [batch][T][J], [batch][pooled].
+ *        ratios: optional [batch][max_steps] injected Beta draws (predict == 0); null -> Beta mode (predict == 1). */
+int tpdm_sample_begin(tpdm_plan* plan, const float* latents, const float* neg_embeds, const float* pos_embeds,
+                      const float* neg_pooled, const float* pos_pooled, float guidance_scale, int predict,
+                      const float* ratios, void* stream);
+/* one denoising step `step` (0-based): MMDiT -> CFG -> TPM -> schedule update -> Euler.  No host synchronisation. */
+int tpdm_sample_step(tpdm_plan* plan, int step, void* stream);
+/* device-resident results; all [batch][max_steps] row-major unless stated */
+typedef struct tpdm_sample_state {
+  float* latents;        /* [batch][C][h][w] current latents (fp32 master copy) */
+  float* velocity;       /* [batch][C][h][w] CFG-combined velocity of the last step */
+  float* sigma_hist;     /* [batch][max_steps+1]: column 0 = 1, column k+1 = sigma_next of step k */
+  float* alphas;
+  float* betas;
+  float* logprobs;       /* raw (un-masked) log-prob */
+  int32_t* prob_masks;
+  int32_t* all_done;     /* [max_steps]: 1 when every sigma_next < min_sigma after that step (modeling_sd3_pnt.py:608) */
+  float* tembs;          /* [max_steps][batch][D] CFG-combined temb per step */
+  void* tpm_input;       /* bf16 [batch][g][g][2D] NHWC scrambled TPM input of the last step */
+  float* history_latents;/* [max_steps][batch][C][h][w] */
+} tpdm_sample_state;
+int tpdm_sample_state_get(tpdm_plan* plan, tpdm_sample_state* out);
+
+/* ---- unit entry points used by tests/ (one kernel each) ---------------------------------------------------------- */
+/* out = epilogue(A[batch][rows][K] (bf16) . W[N][K]^T (bf16)); epi: 0 bias->bf16, 1 bias->f32, 2 bias+gelu->bf16,
+ * 3 out(f32) += gate[batch][N] * (acc + bias) */
+int tpdm_gemm_bf16(const void* A, const void* W, const float* bias, const float* gate, void* out, int batch, int rows,
+                   int N, int K, int epi, void* stream);
+/* qkv bf16 [Bt][S][3*H*dp] -> out bf16 [Bt][S][H*dp] */
+int tpdm_joint_attention(const void* qkv, void* out, int Bt, int S, int H, int dp, int head_dim, int q_rows, void* stream);
+/* conv3x3 pad 1 over NHWC bf16 x [batch][g][g][C], w bf16 [N][9][C] -> out fp32 [batch][g*g][N] */
+int tpdm_conv3x3_nhwc(const void* x, const void* w, const float* bias, float* out, int batch, int g, int C, int N,
+                      void* stream);
+/* LayerNorm(eps 1e-6, no affine) * (1 + scale[b]) + shift[b] : x fp32 [batch][rows][D] -> bf16 */
+int tpdm_ln_modulate(const float* x, const float* shift, const float* scale, int mod_stride, void* out_bf16, int batch,
+                     int rows, int D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPDM_B200_H_ */

@@ -1,0 +1,124 @@
+"""Diagnostic sweep of the tcgen05 kernels against torch fp32 on the GPU box (prints, never asserts)."""
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tpdm_b200 import _lib as L  # noqa: E402
+
+lib = L.load()
+dev = "cuda"
+torch.manual_seed(0)
+
+
+def rel(a, b):
+    return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-30))
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def gemm_case(batch, rows, N, K, epi, time_it=False):
+    A = (torch.randn(batch, rows, K, device=dev) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    gate = torch.randn(batch, N, device=dev)
+    acc = A.float() @ W.float().t() + bias
+    if epi == 0:
+        out = torch.zeros(batch, rows, N, device=dev, dtype=torch.bfloat16); ref = acc
+    elif epi == 1:
+        out = torch.zeros(batch, rows, N, device=dev); ref = acc
+    elif epi == 2:
+        out = torch.zeros(batch, rows, N, device=dev, dtype=torch.bfloat16); ref = torch.nn.functional.gelu(acc, approximate="tanh")
+    else:
+        out = torch.randn(batch, rows, N, device=dev); ref = out + gate[:, None, :] * acc
+    st = lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gate), L.ptr(out), batch, rows, N, K, epi, None)
+    torch.cuda.synchronize()
+    msg = f"gemm b={batch} rows={rows} N={N} K={K} epi={epi}: status={st} rel={rel(out, ref):.3e} maxabs={float((out.float()-ref).abs().max()):.3e}"
+    if time_it and epi != 3:
+        ms = timeit(lambda: lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gate), L.ptr(out), batch, rows, N, K, epi, None))
+        msg += f"  {ms*1e3:.1f} us  {2*batch*rows*N*K/ms/1e9:.1f} TFLOP/s"
+    print(msg, flush=True)
+    if rel(out, ref) > 2e-2:
+        print("   out[0,0,:8] =", out[0, 0, :8].float().tolist())
+        print("   ref[0,0,:8] =", ref[0, 0, :8].float().tolist())
+        print("   out[0,5,64:72] =", out[0, min(5, rows - 1), 64:72].float().tolist())
+        print("   ref[0,5,64:72] =", ref[0, min(5, rows - 1), 64:72].float().tolist())
+
+
+def attn_case(Bt, S, H, d, q_rows=0, time_it=False):
+    dp = 64 if d <= 64 else 128
+    qkv = torch.zeros(Bt, S, 3, H, dp, device=dev)
+    qkv[..., :d] = torch.randn(Bt, S, 3, H, d, device=dev)
+    qkv = qkv.bfloat16().contiguous()
+    out = torch.zeros(Bt, S, H, dp, device=dev, dtype=torch.bfloat16)
+    q, k, v = (qkv[:, :, i, :, :d].float().transpose(1, 2) for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2)  # Bt,S,H,d
+    st = lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, dp, d, q_rows, None)
+    torch.cuda.synchronize()
+    rows = q_rows if q_rows else S
+    o = out[:, :rows, :, :d]
+    msg = f"attn Bt={Bt} S={S} H={H} d={d} q_rows={q_rows}: status={st} rel={rel(o, ref[:, :rows]):.3e} pad_abs={float(out[..., d:].float().abs().max()) if dp > d else 0:.1e}"
+    if time_it:
+        ms = timeit(lambda: lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, dp, d, q_rows, None))
+        msg += f"  {ms*1e3:.1f} us  {4*Bt*H*S*S*d/ms/1e9:.1f} TFLOP/s"
+    print(msg, flush=True)
+    if rel(o, ref[:, :rows]) > 2e-2:
+        print("   out[0,0,0,:8] =", out[0, 0, 0, :8].float().tolist())
+        print("   ref[0,0,0,:8] =", ref[0, 0, 0, :8].float().tolist())
+        print("   out[0,S-1,0,:8] =", out[0, S - 1, 0, :8].float().tolist())
+        print("   ref[0,S-1,0,:8] =", ref[0, S - 1, 0, :8].float().tolist())
+
+
+def conv_case(B, g, Cc, N):
+    x = torch.randn(B, Cc, g, g, device=dev).bfloat16()
+    w = (torch.randn(N, Cc, 3, 3, device=dev) * 0.05).bfloat16()
+    bias = torch.randn(N, device=dev)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B, g * g, N)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * Cc).contiguous()
+    out = torch.zeros(B, g * g, N, device=dev)
+    st = lib.tpdm_conv3x3_nhwc(L.ptr(xn), L.ptr(wp), L.ptr(bias), L.ptr(out), B, g, Cc, N, None)
+    torch.cuda.synchronize()
+    print(f"conv3x3 B={B} g={g} C={Cc} N={N}: status={st} rel={rel(out, ref):.3e}", flush=True)
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0), flush=True)
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "gemm"):
+        gemm_case(1, 128, 256, 64, 1)
+        gemm_case(1, 128, 256, 256, 1)
+        gemm_case(1, 256, 512, 512, 0)
+        gemm_case(2, 333, 384, 384, 0)
+        gemm_case(2, 333, 1152, 384, 2)
+        gemm_case(2, 256, 384, 1536, 3)
+        gemm_case(2, 256, 64, 384, 1)
+        gemm_case(2, 4096, 4608, 1536, 0, True)
+        gemm_case(2, 4096, 6144, 1536, 2, True)
+        gemm_case(2, 4096, 1536, 6144, 3)
+        gemm_case(2, 4096, 1536, 6144, 1, True)
+    if which in ("all", "conv"):
+        conv_case(2, 16, 128, 128)
+        conv_case(1, 64, 3072, 128)
+        conv_case(1, 128, 256, 128)
+    if which in ("all", "attn"):
+        attn_case(1, 128, 1, 64)
+        attn_case(1, 256, 2, 64)
+        attn_case(2, 589, 4, 96)
+        attn_case(1, 1357, 4, 64)
+        attn_case(1, 1357, 4, 64, q_rows=1024)
+        attn_case(2, 4429, 24, 64, 0, True)
+    print("diag done", flush=True)

@@ -1,0 +1,112 @@
+"""ctypes binding of libtpdm_b200.so (include/tpdm_b200.h).  There is no fallback: if the shared library is missing
+or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtpdm_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+vp = C.c_void_p
+
+TPDM_OK, TPDM_ERR_ARG, TPDM_ERR_SHAPE, TPDM_ERR_CUDA, TPDM_ERR_STATE, TPDM_ERR_NOMEM = 0, -1, -2, -3, -4, -5
+
+
+class TpdmConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "num_layers", "num_heads", "head_dim", "joint_attention_dim", "pooled_projection_dim", "in_channels",
+        "out_channels", "patch_size", "pos_embed_max_size", "qk_norm", "tpm_channels", "prediction_type", "relative")
+    ] + [("min_sigma", C.c_float), ("epsilon", C.c_float), ("tpm_epsilon", C.c_float)]
+
+
+BLOCK_FIELDS = ("qkv_w", "qkv_b", "cqkv_w", "cqkv_b", "out_w", "out_b", "cout_w", "cout_b", "ff1_w", "ff1_b", "ff2_w",
+                "ff2_b", "cff1_w", "cff1_b", "cff2_w", "cff2_b", "norm_q", "norm_k", "norm_added_q", "norm_added_k")
+
+
+class TpdmBlockWeights(C.Structure):
+    _fields_ = [(n, vp) for n in BLOCK_FIELDS]
+
+
+GLOBAL_FIELDS_A = ("patch_w", "patch_b", "pos_table", "t_w1", "t_b1", "t_w2", "t_b2", "p_w1", "p_b1", "p_w2", "p_b2",
+                   "ctx_w", "ctx_b", "adaln_w", "adaln_b", "proj_w", "proj_b")
+GLOBAL_FIELDS_B = ("tpm_conv1_w", "tpm_conv1_b", "tpm_lin_w", "tpm_lin_b", "tpm_gn_w", "tpm_gn_b", "tpm_conv2_w",
+                   "tpm_conv2_b", "tpm_fc1_w", "tpm_fc1_b", "tpm_fc2_w", "tpm_fc2_b")
+
+
+class TpdmWeights(C.Structure):
+    _fields_ = [(n, vp) for n in GLOBAL_FIELDS_A] + [("blocks", C.POINTER(TpdmBlockWeights))] + [(n, vp) for n in GLOBAL_FIELDS_B]
+
+
+class TpdmSampleState(C.Structure):
+    _fields_ = [(n, vp) for n in ("latents", "velocity", "sigma_hist", "alphas", "betas", "logprobs", "prob_masks",
+                                  "all_done", "tembs", "tpm_input", "history_latents")]
+
+
+EXPORTS = {
+    "tpdm_last_error": (C.c_char_p, []),
+    "tpdm_abi_version": (C.c_int, []),
+    "tpdm_create": (C.c_int, [C.POINTER(TpdmConfig), C.POINTER(vp)]),
+    "tpdm_destroy": (C.c_int, [vp]),
+    "tpdm_set_weights": (C.c_int, [vp, C.POINTER(TpdmWeights)]),
+    "tpdm_plan_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "tpdm_plan_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(vp)]),
+    "tpdm_plan_destroy": (C.c_int, [vp]),
+    "tpdm_mmdit_forward": (C.c_int, [vp] + [vp] * 8 + [vp]),
+    "tpdm_tpm_forward": (C.c_int, [vp, vp, vp, vp, vp]),
+    "tpdm_euler_step": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_longlong, vp]),
+    "tpdm_sample_begin": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp]),
+    "tpdm_sample_step": (C.c_int, [vp, C.c_int, vp]),
+    "tpdm_sample_state_get": (C.c_int, [vp, C.POINTER(TpdmSampleState)]),
+    "tpdm_gemm_bf16": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tpdm_joint_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tpdm_conv3x3_nhwc": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tpdm_ln_modulate": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the C-ABI library; raises RuntimeError if it has not been built (python -m tpdm_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m tpdm_b200.build` "
+                               "(tpdm_b200 has no CPU / PyTorch fallback)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        if lib.tpdm_abi_version() != 1:
+            raise RuntimeError("libtpdm_b200.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def check(status: int) -> None:
+    if status == TPDM_OK:
+        return
+    msg = load().tpdm_last_error().decode("utf-8", "replace")
+    if status in (TPDM_ERR_ARG, TPDM_ERR_SHAPE):
+        raise ValueError(msg)
+    raise RuntimeError(f"libtpdm_b200 error {status}: {msg}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL).  The tensor must be CUDA and contiguous."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("tpdm_b200 needs CUDA tensors (there is no CPU path)")
+    if not t.is_contiguous():
+        raise ValueError("tpdm_b200 needs contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,330 @@
+// tpdm_b200 -- persistent, warp-specialised bf16 GEMM on tcgen05 tensor cores (sm_100a).
+//
+//   out = epilogue( A[rows x K] . W[N x K]^T )        fp32 accumulation in TMEM
+//
+// Replaces every nn.Linear on the MMDiT path (diffusers to_q/to_k/to_v, add_*_proj, to_out, to_add_out, ff.net.*,
+// context_embedder, proj_out; call sites /root/reference/src/models/stable_diffusion_3/transformer_sd3.py:337,361,374)
+// and, in conv mode, TimePredictor.conv1 (modeling_sd3_pnt.py:88,104) as a 9-tap implicit GEMM.
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0     TMA producer: A tile 128x64 and W tile BNx64 (bf16, 128B swizzle) into a 4-stage smem ring
+//   warp 1     MMA issuer: one elected lane issues 4 x tcgen05.mma (128 x BN x 16) per stage into a double-buffered
+//              TMEM accumulator (2 x BN columns), tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 2-5  epilogue: tcgen05.ld 32 rows x 32 cols per warp, transpose through padded smem so that global traffic is
+//              row-contiguous, then bias / GELU-tanh / gate*x + fp32 residual
+// Up to two independent problems (image stream + text stream) share one launch so the small text GEMM fills the tail wave.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "host.h"
+
+namespace tpdm {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;
+constexpr int kABytes = BM * BK * 2;
+constexpr int kStagePad = 33;  // floats per staged row
+
+struct GemmParams {
+  GemmOp op[2];
+  int n_ops;
+  int total_tiles;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRing = kStages * kStageBytes;
+  static constexpr int kEpi = 4 * 32 * kStagePad * 4;
+  static constexpr int kBarOff = kRing + kEpi;
+  static constexpr int kTotal = kBarOff + 256 + 1024;  // + barriers + alignment slack
+};
+
+struct TileCoord {
+  int g, b, mt, nt;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) {
+  TileCoord t;
+  t.g = (P.n_ops > 1 && tile >= P.op[0].num_tiles) ? 1 : 0;
+  int local = tile - (t.g ? P.op[0].num_tiles : 0);
+  const GemmOp& G = P.op[t.g];
+  int m_tiles = G.batch * G.tiles_m_per_batch;
+  int m_idx = local % m_tiles;
+  t.nt = local / m_tiles;
+  t.b = m_idx / G.tiles_m_per_batch;
+  t.mt = m_idx % G.tiles_m_per_batch;
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams P) {
+  using L = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi_stage = reinterpret_cast<float*>(smem + L::kRing);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full = empty_bar + kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < P.n_ops; ++i) {
+      tma_prefetch_desc(&P.op[i].tmA);
+      tma_prefetch_desc(&P.op[i].tmB);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<2 * BN>(tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(P, tile);
+        const GemmOp& G = P.op[tc.g];
+        const int nkb = (G.K + BK - 1) / BK;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * L::kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (G.conv) {
+            const int tap = kb / G.kb_per_tap;
+            const int c0 = (kb - tap * G.kb_per_tap) * BK;
+            tma_load_4d(sA, &G.tmA, &full_bar[stage], c0, tap % 3 - 1, tc.mt * G.conv_by + tap / 3 - 1, tc.b);
+          } else {
+            tma_load_3d(sA, &G.tmA, &full_bar[stage], kb * BK, tc.mt * BM, tc.b);
+          }
+          tma_load_2d(sB, &G.tmB, &full_bar[stage], kb * BK, tc.nt * BN);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(P, tile);
+      const GemmOp& G = P.op[tc.g];
+      const int nkb = (G.K + BK - 1) / BK;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_base = a_base + kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    float* st = epi_stage + (warp - 2) * 32 * kStagePad;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(P, tile);
+      const GemmOp& G = P.op[tc.g];
+      const int n0 = tc.nt * BN;
+      const int row_base = tc.mt * BM + q * 32;
+      int n_chunks = (G.N - n0 + 31) / 32;
+      n_chunks = n_chunks > BN / 32 ? BN / 32 : n_chunks;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      for (int c = 0; c < n_chunks; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_wait_ld();
+        if (c == n_chunks - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) st[lane * kStagePad + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const int col = n0 + c * 32 + lane;
+        const bool col_ok = col < G.N;
+        const float bias = (col_ok && G.bias) ? G.bias[col] : 0.f;
+        int rows = G.rows_per_batch - row_base;
+        rows = rows > 32 ? 32 : rows;
+        if (col_ok && rows > 0) {
+          const long long o0 = static_cast<long long>(tc.b) * G.out_batch_stride + static_cast<long long>(row_base) * G.ldo + col;
+          if (G.epi == EPI_BIAS_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + o0;
+            for (int r = 0; r < rows; ++r) o[static_cast<long long>(r) * G.ldo] = __float2bfloat16(st[r * kStagePad + lane] + bias);
+          } else if (G.epi == EPI_BIAS_GELU_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + o0;
+            for (int r = 0; r < rows; ++r)
+              o[static_cast<long long>(r) * G.ldo] = __float2bfloat16(gelu_tanh(st[r * kStagePad + lane] + bias));
+          } else if (G.epi == EPI_BIAS_F32) {
+            float* o = reinterpret_cast<float*>(G.out) + o0;
+            for (int r = 0; r < rows; ++r) o[static_cast<long long>(r) * G.ldo] = st[r * kStagePad + lane] + bias;
+          } else {  // EPI_GATE_RESIDUAL
+            float* o = reinterpret_cast<float*>(G.out) + o0;
+            const float gate = G.gate[static_cast<long long>(tc.b) * G.gate_stride + col];
+            for (int r = 0; r < rows; ++r) {
+              float* p = o + static_cast<long long>(r) * G.ldo;
+              *p = *p + gate * (st[r * kStagePad + lane] + bias);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<2 * BN>(tmem_base);
+}
+
+template <int BN>
+int launch_impl(const GemmParams& P, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TPDM_CUDA_OK(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      GemmSmem<BN>::kTotal));
+    attr_set = true;
+  }
+  int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(P);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int finish_op(GemmOp* op, const void* W, int N, int K, int epi, void* out, long long out_batch_stride, int ldo,
+              const float* bias, const float* gate, int gate_stride) {
+  op->N = N;
+  op->K = K;
+  op->block_n = N <= 128 ? 128 : 256;
+  op->tiles_n = (N + op->block_n - 1) / op->block_n;
+  op->num_tiles = op->batch * op->tiles_m_per_batch * op->tiles_n;
+  op->epi = epi;
+  op->out = out;
+  op->out_batch_stride = out_batch_stride;
+  op->ldo = ldo;
+  op->bias = bias;
+  op->gate = gate;
+  op->gate_stride = gate_stride;
+  TPDM_CHECK(K % 8 == 0, TPDM_ERR_SHAPE, "gemm: K=%d must be a multiple of 8", K);
+  TPDM_CHECK(epi != EPI_GATE_RESIDUAL || gate != nullptr, TPDM_ERR_ARG, "gemm: gate pointer required");
+  uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+  uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+  uint32_t box[2] = {BK, static_cast<uint32_t>(op->block_n)};
+  return encode_tmap_bf16(&op->tmB, W, 2, dims, strides, box);
+}
+
+}  // namespace
+
+int gemm_op_init(GemmOp* op, const void* A, long long a_row_stride, long long a_batch_stride, int rows_per_batch, int batch,
+                 int K, const void* W, int N, int epi, void* out, long long out_batch_stride, int ldo, const float* bias,
+                 const float* gate, int gate_stride) {
+  *op = GemmOp{};
+  TPDM_CHECK(rows_per_batch > 0 && batch > 0 && K > 0 && N > 0, TPDM_ERR_SHAPE, "gemm: empty problem");
+  op->rows_per_batch = rows_per_batch;
+  op->batch = batch;
+  op->tiles_m_per_batch = (rows_per_batch + BM - 1) / BM;
+  op->conv = 0;
+  uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(rows_per_batch), static_cast<uint64_t>(batch)};
+  uint64_t strides[2] = {static_cast<uint64_t>(a_row_stride) * 2,
+                         static_cast<uint64_t>(batch > 1 ? a_batch_stride : a_row_stride * rows_per_batch) * 2};
+  uint32_t box[3] = {BK, BM, 1};
+  TPDM_TRY(encode_tmap_bf16(&op->tmA, A, 3, dims, strides, box));
+  return finish_op(op, W, N, K, epi, out, out_batch_stride, ldo, bias, gate, gate_stride);
+}
+
+int gemm_op_init_conv3x3(GemmOp* op, const void* X, int batch, int g, int C, const void* W, int N, int epi, void* out,
+                         int ldo, const float* bias) {
+  *op = GemmOp{};
+  TPDM_CHECK(g >= 8 && g <= 128 && (g & (g - 1)) == 0, TPDM_ERR_SHAPE, "conv3x3: grid side %d must be a power of two in [8,128]", g);
+  TPDM_CHECK(C % BK == 0, TPDM_ERR_SHAPE, "conv3x3: C=%d must be a multiple of 64", C);
+  op->rows_per_batch = g * g;
+  op->batch = batch;
+  op->tiles_m_per_batch = (g * g + BM - 1) / BM;
+  op->conv = 1;
+  op->conv_by = BM / g;
+  op->kb_per_tap = C / BK;
+  uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(g), static_cast<uint64_t>(g), static_cast<uint64_t>(batch)};
+  uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * g * 2, static_cast<uint64_t>(C) * g * g * 2};
+  uint32_t box[4] = {BK, static_cast<uint32_t>(g), static_cast<uint32_t>(BM / g), 1};
+  TPDM_TRY(encode_tmap_bf16(&op->tmA, X, 4, dims, strides, box));
+  return finish_op(op, W, N, 9 * C, epi, out, static_cast<long long>(g) * g * ldo, ldo, bias, nullptr, 0);
+}
+
+int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {
+  TPDM_CHECK(n_ops >= 1 && n_ops <= 2, TPDM_ERR_ARG, "gemm_launch: 1 or 2 ops per launch");
+  GemmParams P;
+  P.n_ops = n_ops;
+  P.total_tiles = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    P.op[i] = ops[i];
+    P.total_tiles += ops[i].num_tiles;
+    TPDM_CHECK(ops[i].block_n == ops[0].block_n, TPDM_ERR_ARG, "gemm_launch: grouped ops must share the N tile");
+  }
+  if (n_ops == 1) P.op[1] = ops[0];
+  return ops[0].block_n == 128 ? launch_impl<128>(P, stream) : launch_impl<256>(P, stream);
+}
+
+}  // namespace tpdm

@@ -1,0 +1,89 @@
+// tpdm_b200 -- host-side helpers shared by the translation units of libtpdm_b200.so
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/tpdm_b200.h"
+
+namespace tpdm {
+
+void set_last_error(const std::string& msg);
+int fail(int code, const char* fmt, ...);
+
+#define TPDM_CUDA_OK(expr)                                                                           \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::tpdm::fail(TPDM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define TPDM_CHECK(cond, code, ...)                     \
+  do {                                                  \
+    if (!(cond)) return ::tpdm::fail(code, __VA_ARGS__); \
+  } while (0)
+
+#define TPDM_TRY(expr)       \
+  do {                       \
+    int _s = (expr);         \
+    if (_s != 0) return _s;  \
+  } while (0)
+
+int num_sms();
+
+// bf16 tiled tensor map with 128-byte swizzle.  dims/strides innermost first; strides (bytes) for dims 1..rank-1.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                     const uint32_t* box);
+
+// ------------------------------------------------------------------------------------------------------------
+// GEMM  (gemm_tcgen05.cu):  out = epilogue(A[rows x K] * W[N x K]^T)
+// ------------------------------------------------------------------------------------------------------------
+enum GemmEpilogue : int {
+  EPI_BIAS_BF16 = 0,       // out(bf16) = acc + bias
+  EPI_BIAS_F32 = 1,        // out(f32)  = acc + bias
+  EPI_BIAS_GELU_BF16 = 2,  // out(bf16) = gelu_tanh(acc + bias)
+  EPI_GATE_RESIDUAL = 3,   // out(f32) += gate[b, n] * (acc + bias)
+};
+
+struct alignas(64) GemmOp {
+  CUtensorMap tmA;  // normal: (K, rows_per_batch, batch) box (64,128,1); conv: (C, x, y, b) box (64, g, 128/g, 1)
+  CUtensorMap tmB;  // (K, N) box (64, BN)
+  int rows_per_batch, batch, N, K;
+  int tiles_m_per_batch, tiles_n, num_tiles, block_n;
+  int conv, conv_by, kb_per_tap, epi;
+  void* out;
+  long long out_batch_stride;  // elements between batches of the output
+  int ldo;                     // output leading dimension (elements)
+  int gate_stride;             // elements between batches of gate
+  const float* bias;           // [N] or null
+  const float* gate;           // [batch][gate_stride] (EPI_GATE_RESIDUAL)
+};
+
+// A: bf16, element (b, r, k) at A + b*a_batch_stride + r*a_row_stride + k.   W: bf16 [N][K] row-major.
+int gemm_op_init(GemmOp* op, const void* A, long long a_row_stride, long long a_batch_stride, int rows_per_batch, int batch,
+                 int K, const void* W, int N, int epi, void* out, long long out_batch_stride, int ldo, const float* bias,
+                 const float* gate, int gate_stride);
+// implicit-GEMM 3x3 / pad 1 / stride 1 convolution over NHWC bf16 X[b][g][g][C]; W packed [N][9*C] (tap-major, tap=ky*3+kx).
+int gemm_op_init_conv3x3(GemmOp* op, const void* X, int batch, int g, int C, const void* W, int N, int epi, void* out,
+                         int ldo, const float* bias);
+// one persistent launch over up to two ops (e.g. image stream + text stream)
+int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------------------
+// joint attention (attention_tcgen05.cu)
+// ------------------------------------------------------------------------------------------------------------
+struct alignas(64) AttnOp {
+  CUtensorMap tmQ, tmK, tmV;  // (dp, S, H, Bt) views of the token-major qkv buffer, box (64, 128, 1, 1)
+  int S, H, Bt, dp;           // dp = padded head dim (64 or 128)
+  int q_tiles;
+  float scale_log2;           // log2(e) / sqrt(head_dim)
+  __nv_bfloat16* out;         // [Bt][S][H*dp]
+};
+int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int head_dim, void* out);
+int attn_launch(const AttnOp* op, cudaStream_t stream);
+
+}  // namespace tpdm

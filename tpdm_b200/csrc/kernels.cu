@@ -1,0 +1,678 @@
+// tpdm_b200 -- bandwidth-bound kernels of the TPDM step (sm_100a): vectorised, coalesced, warp-shuffle reduced.
+// Each kernel names the reference code it replaces (paths relative to /root/reference).
+#include <math.h>
+
+#include "common.cuh"
+#include "host.h"
+#include "kernels.h"
+
+namespace tpdm {
+
+namespace {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float bf16lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// token n of a g x g grid -> pixel index after reshape_hidden_states_to_2d (modeling_sd3_pnt.py:33-54)
+__device__ __forceinline__ int scramble_pixel(int n, int g) {
+  const int y = 2 * (n / (2 * g)) + ((n & 3) >> 1);
+  const int x = 2 * ((n % (2 * g)) >> 2) + (n & 1);
+  return y * g + x;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  for (; i + 3 < n; i += stride) {
+    float4 v = ld4(in + i);
+    uint2 w;
+    w.x = pack_bf16x2(v.x, v.y);
+    w.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = w;
+  }
+  if (i < n)
+    for (long long k = i; k < n && k < i + 4; ++k) out[k] = __float2bfloat16(in[k]);
+}
+
+// diffusers get_timestep_embedding (call site transformer_sd3.py:336)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int t_stride, float scale, float* __restrict__ out, int Bt,
+                                          int rep) {
+  const int b = blockIdx.x;
+  const int i = threadIdx.x;  // 0..127
+  const float ts = t[(b % (Bt / rep)) * t_stride] * scale;
+  const float f = expf(-logf(10000.0f) * static_cast<float>(i) / 128.0f);
+  const float a = ts * f;
+  out[b * 256 + i] = cosf(a);
+  out[b * 256 + 128 + i] = sinf(a);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GEMV family: adaLN modulation linears of all blocks in one launch, time/text embedders, TPM norm1.linear
+// (diffusers AdaLayerNormZero/Continuous .linear, TimestepEmbedding, PixArtAlphaTextProjection; K6/K4 of SURVEY 2.2)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kGemvNB = 8;         // batch rows held per pass
+constexpr int kGemvRowsPerWarp = 4;
+constexpr int kGemvWarps = 8;
+
+template <typename WT>
+__global__ void __launch_bounds__(kGemvWarps * 32) gemv_kernel(const WT* __restrict__ W, const float* __restrict__ bias,
+                                                                const float* __restrict__ x, int ldx,
+                                                                const float* __restrict__ addend, float* __restrict__ y, int ldy,
+                                                                int Bt, int J, int K, int act) {
+  extern __shared__ float xs[];  // [nb][K]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j0 = (blockIdx.x * kGemvWarps + warp) * kGemvRowsPerWarp;
+  for (int b0 = 0; b0 < Bt; b0 += kGemvNB) {
+    const int nb = min(kGemvNB, Bt - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nb * K; i += blockDim.x) {
+      const int bb = i / K, k = i - bb * K;
+      float v = x[static_cast<long long>(b0 + bb) * ldx + k];
+      xs[i] = act ? silu_f(v) : v;
+    }
+    __syncthreads();
+    for (int r = 0; r < kGemvRowsPerWarp; ++r) {
+      const int j = j0 + r;
+      if (j >= J) break;
+      float acc[kGemvNB];
+#pragma unroll
+      for (int bb = 0; bb < kGemvNB; ++bb) acc[bb] = 0.f;
+      const WT* wrow = W + static_cast<long long>(j) * K;
+      constexpr int EPL = 16 / sizeof(WT);  // elements per 16-byte load
+      for (int k = lane * EPL; k < K; k += 32 * EPL) {
+        float w[EPL];
+        const uint4 raw = ldg_nc_u4(wrow + k);
+        if constexpr (sizeof(WT) == 2) {
+          w[0] = bf16lo(raw.x); w[1] = bf16hi(raw.x); w[2] = bf16lo(raw.y); w[3] = bf16hi(raw.y);
+          w[4] = bf16lo(raw.z); w[5] = bf16hi(raw.z); w[6] = bf16lo(raw.w); w[7] = bf16hi(raw.w);
+        } else {
+          w[0] = __uint_as_float(raw.x); w[1] = __uint_as_float(raw.y); w[2] = __uint_as_float(raw.z); w[3] = __uint_as_float(raw.w);
+        }
+#pragma unroll
+        for (int bb = 0; bb < kGemvNB; ++bb) {
+          if (bb < nb) {
+            const float* xp = xs + bb * K + k;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) acc[bb] = fmaf(w[e], xp[e], acc[bb]);
+          }
+        }
+      }
+#pragma unroll
+      for (int bb = 0; bb < kGemvNB; ++bb) {
+        if (bb < nb) {
+          const float s = warp_sum(acc[bb]);
+          if (lane == 0) {
+            const long long o = static_cast<long long>(b0 + bb) * ldy + j;
+            y[o] = s + (bias ? bias[j] : 0.f) + (addend ? addend[o] : 0.f);
+          }
+        }
+      }
+    }
+  }
+}
+
+template <typename WT>
+int gemv_launch(const WT* W, const float* bias, const float* x, int ldx, const float* addend, float* y, int ldy, int Bt, int J, int K,
+                int act, cudaStream_t s) {
+  constexpr int EPL = 16 / sizeof(WT);
+  TPDM_CHECK(K % EPL == 0, TPDM_ERR_SHAPE, "gemv: K=%d must be a multiple of %d", K, EPL);
+  const int nb = Bt < kGemvNB ? Bt : kGemvNB;
+  const size_t smem = static_cast<size_t>(nb) * K * sizeof(float);
+  TPDM_CHECK(smem <= 160 * 1024, TPDM_ERR_SHAPE, "gemv: K=%d too large", K);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    TPDM_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    smem_set = 160 * 1024;
+  }
+  const int rows_per_block = kGemvWarps * kGemvRowsPerWarp;
+  gemv_kernel<WT><<<(J + rows_per_block - 1) / rows_per_block, kGemvWarps * 32, smem, s>>>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// PatchEmbed (diffusers; call site transformer_sd3.py:334) + hidden_states_1 tap (:335)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kPatchTok = 32;
+
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ lat, const float* __restrict__ Wp,
+                                                       const float* __restrict__ bias, const float* __restrict__ pos, int pos_max,
+                                                       float* __restrict__ x, int Bl, int dup, int C, int Hl, int Wl, int D,
+                                                       float* __restrict__ h1_out, bf16* __restrict__ tpm_x) {
+  extern __shared__ float in_s[];  // [kPatchTok][C*4]
+  const int gw = Wl / 2, gh = Hl / 2, N = gw * gh;
+  const int KK = C * 4;
+  const int bl = blockIdx.y;
+  const int n0 = blockIdx.x * kPatchTok;
+  for (int i = threadIdx.x; i < kPatchTok * KK; i += blockDim.x) {
+    const int t = i / KK, k = i - t * KK;
+    const int c = k >> 2, p = (k >> 1) & 1, q = k & 1;
+    const int n = n0 + t;
+    const int ty = n / gw, tx = n - ty * gw;
+    in_s[i] = lat[((static_cast<long long>(bl) * C + c) * Hl + 2 * ty + p) * Wl + 2 * tx + q];
+  }
+  __syncthreads();
+  const int top = (pos_max - gh) / 2, left = (pos_max - gw) / 2;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float w[64];
+    const float* wr = Wp + static_cast<long long>(d) * KK;
+#pragma unroll
+    for (int k = 0; k < 64; k += 4) {
+      float4 v = ld4(wr + k);
+      w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
+    }
+    const float bs = bias[d];
+    for (int t = 0; t < kPatchTok; ++t) {
+      const int n = n0 + t;
+      const int ty = n / gw, tx = n - ty * gw;
+      float acc = bs;
+      const float* ip = in_s + t * KK;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) acc = fmaf(w[k], ip[k], acc);
+      acc += pos[(static_cast<long long>(top + ty) * pos_max + left + tx) * D + d];
+      for (int r = 0; r < dup; ++r) {
+        const long long o = (static_cast<long long>(bl + r * Bl) * N + n) * D + d;
+        x[o] = acc;
+        if (h1_out) h1_out[o] = acc;
+      }
+      if (tpm_x) tpm_x[(static_cast<long long>(bl) * N + scramble_pixel(n, gw)) * (2 * D) + d] = __float2bfloat16(acc);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm + adaLN modulation (diffusers AdaLayerNormZero.forward, norm2 + modulate in JointTransformerBlock.forward,
+// AdaLayerNormContinuous; K7/K13).  One warp per token row, fp32 statistics, two-pass variance.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void row_stats(const float* __restrict__ row, int D, int lane, float& mean, float& rstd) {
+  float s = 0.f;
+  for (int k = lane * 4; k < D; k += 128) {
+    float4 v = ld4(row + k);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  mean = warp_sum(s) / D;
+  float ss = 0.f;
+  for (int k = lane * 4; k < D; k += 128) {
+    float4 v = ld4(row + k);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  rstd = rsqrtf(warp_sum(ss) / D + 1e-6f);
+}
+
+struct LnParams {
+  LnSeg seg[2];
+  int nseg, D;
+  long long rows0, rows_total;
+};
+
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnParams P) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= P.rows_total) return;
+  const int si = r >= P.rows0 ? 1 : 0;
+  const LnSeg& S = P.seg[si];
+  const long long lr = r - (si ? P.rows0 : 0);
+  const int b = static_cast<int>(lr / S.rows);
+  const float* row = S.x + lr * P.D;
+  float mean, rstd;
+  row_stats(row, P.D, lane, mean, rstd);
+  const float* sh = S.shift + static_cast<long long>(b) * S.mod_stride;
+  const float* sc = S.scale + static_cast<long long>(b) * S.mod_stride;
+  bf16* o = S.out + lr * P.D;
+  for (int k = lane * 4; k < P.D; k += 128) {
+    const float4 v = ld4(row + k), h = ld4(sh + k), c = ld4(sc + k);
+    uint2 w;
+    w.x = pack_bf16x2((v.x - mean) * rstd * (1.f + c.x) + h.x, (v.y - mean) * rstd * (1.f + c.y) + h.y);
+    w.y = pack_bf16x2((v.z - mean) * rstd * (1.f + c.z) + h.z, (v.w - mean) * rstd * (1.f + c.w) + h.w);
+    *reinterpret_cast<uint2*>(o + k) = w;
+  }
+}
+
+// norm_out (transformer_sd3.py:372-373) fused with the CFG combine of hidden_states_2 (modeling_sd3_pnt.py:545-548) and
+// the token->pixel scramble of reshape_hidden_states_to_2d (:551).
+__global__ void __launch_bounds__(256) norm_out_kernel(const float* __restrict__ x, bf16* __restrict__ xn,
+                                                       const float* __restrict__ shift, const float* __restrict__ scale,
+                                                       int mod_stride, int B, int cfg_pairs, int N, int D, int g, float guidance,
+                                                       bf16* __restrict__ tpm_x, float* __restrict__ h2_out) {
+  const int lane = threadIdx.x & 31;
+  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= static_cast<long long>(B) * N) return;
+  const int bl = static_cast<int>(r / N), n = static_cast<int>(r - static_cast<long long>(bl) * N);
+  const int halves = cfg_pairs ? 2 : 1;
+  float mean[2], rstd[2];
+  const float* row[2];
+  for (int hf = 0; hf < halves; ++hf) {
+    row[hf] = x + (static_cast<long long>(bl + hf * B) * N + n) * D;
+    row_stats(row[hf], D, lane, mean[hf], rstd[hf]);
+  }
+  const long long pix = tpm_x ? (static_cast<long long>(bl) * N + scramble_pixel(n, g)) * (2 * D) + D : 0;
+  for (int k = lane * 4; k < D; k += 128) {
+    float y[2][4];
+    for (int hf = 0; hf < halves; ++hf) {
+      const int bb = bl + hf * B;
+      const float4 v = ld4(row[hf] + k), h = ld4(shift + static_cast<long long>(bb) * mod_stride + k),
+                   c = ld4(scale + static_cast<long long>(bb) * mod_stride + k);
+      y[hf][0] = (v.x - mean[hf]) * rstd[hf] * (1.f + c.x) + h.x;
+      y[hf][1] = (v.y - mean[hf]) * rstd[hf] * (1.f + c.y) + h.y;
+      y[hf][2] = (v.z - mean[hf]) * rstd[hf] * (1.f + c.z) + h.z;
+      y[hf][3] = (v.w - mean[hf]) * rstd[hf] * (1.f + c.w) + h.w;
+      const long long o = (static_cast<long long>(bb) * N + n) * D + k;
+      uint2 w;
+      w.x = pack_bf16x2(y[hf][0], y[hf][1]);
+      w.y = pack_bf16x2(y[hf][2], y[hf][3]);
+      *reinterpret_cast<uint2*>(xn + o) = w;
+      if (h2_out) *reinterpret_cast<float4*>(h2_out + o) = make_float4(y[hf][0], y[hf][1], y[hf][2], y[hf][3]);
+    }
+    if (tpm_x) {
+      float c4[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c4[e] = cfg_pairs ? y[0][e] + guidance * (y[1][e] - y[0][e]) : y[0][e];
+      uint2 w;
+      w.x = pack_bf16x2(c4[0], c4[1]);
+      w.y = pack_bf16x2(c4[2], c4[3]);
+      *reinterpret_cast<uint2*>(tpm_x + pix + k) = w;
+    }
+  }
+}
+
+// diffusers RMSNorm on q/k heads (Attention.norm_q / norm_k / norm_added_q / norm_added_k; K9)
+__global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv, int Bt, int S, int row0, int rows, int H, int dp, int d,
+                                                         const float* __restrict__ wq, const float* __restrict__ wk) {
+  const int lane = threadIdx.x & 31;
+  const long long item = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);  // (b, r, which, h)
+  const long long total = static_cast<long long>(Bt) * rows * 2 * H;
+  if (item >= total) return;
+  const int h = static_cast<int>(item % H);
+  const int which = static_cast<int>((item / H) % 2);
+  const long long br = item / (2 * H);
+  const int r = static_cast<int>(br % rows), b = static_cast<int>(br / rows);
+  bf16* p = qkv + (static_cast<long long>(b) * S + row0 + r) * (3LL * H * dp) + static_cast<long long>(which) * H * dp + h * dp;
+  const float* w = which ? wk : wq;
+  float v[4];
+  float ss = 0.f;
+  const int per = dp / 32;  // 2 or 4
+  for (int e = 0; e < per; ++e) {
+    v[e] = __bfloat162float(p[lane * per + e]);
+    ss += v[e] * v[e];
+  }
+  const float rs = rsqrtf(warp_sum(ss) / d + 1e-6f);
+  for (int e = 0; e < per; ++e) p[lane * per + e] = __float2bfloat16(v[e] * rs * w[lane * per + e]);
+}
+
+// unpatchify (transformer_sd3.py:377-399) + CFG combine (modeling_sd3_pnt.py:537-538) + custom_step (model_utilis.py:61-69)
+__global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict__ pout, int B, int cfg_pairs, float guidance, int C,
+                                                         int Hl, int Wl, float* __restrict__ velocity, float* __restrict__ latents,
+                                                         const float* __restrict__ sigma, const float* __restrict__ sigma_next,
+                                                         int sigma_stride, float* __restrict__ history) {
+  const long long total = static_cast<long long>(B) * C * Hl * Wl;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int xx = static_cast<int>(i % Wl);
+  const int yy = static_cast<int>((i / Wl) % Hl);
+  const int c = static_cast<int>((i / (static_cast<long long>(Wl) * Hl)) % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(Wl) * Hl * C));
+  const int gw = Wl / 2, N = gw * (Hl / 2);
+  const int n = (yy >> 1) * gw + (xx >> 1);
+  const int idx = (((yy & 1) << 1) | (xx & 1)) * C + c;
+  float v = pout[(static_cast<long long>(b) * N + n) * (4 * C) + idx];
+  if (cfg_pairs) {
+    const float vc = pout[(static_cast<long long>(b + B) * N + n) * (4 * C) + idx];
+    v = v + guidance * (vc - v);
+  }
+  if (velocity) velocity[i] = v;
+  if (latents) {
+    const float ds = sigma_next[b * sigma_stride] - sigma[b * sigma_stride];
+    const float nv = latents[i] + ds * v;
+    latents[i] = nv;
+    if (history) history[i] = nv;
+  }
+}
+
+__global__ void euler_kernel(const float* __restrict__ v, const float* __restrict__ sn, const float* __restrict__ s0,
+                             const float* __restrict__ x, float* __restrict__ out, int B, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * n) return;
+  const int b = static_cast<int>(i / n);
+  out[i] = x[i] + (sn[b] - s0[b]) * v[i];
+}
+
+__global__ void cfg_combine_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out2, int B, int n,
+                                   float guidance) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * n) return;
+  const float u = in[i], c = in[i + static_cast<long long>(B) * n];
+  const float r = u + guidance * (c - u);
+  out[i] = r;
+  if (out2) out2[i] = r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// TimePredictor tail (modeling_sd3_pnt.py:77-83, 104-115)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ out, int B, int C, int g) {
+  __shared__ float tile[32][33];
+  const int P = g * g;
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < P) ? x[(static_cast<long long>(b) * C + c) * P + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (c < C && p < P) out[(static_cast<long long>(b) * P + p) * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(const float* __restrict__ y, double* __restrict__ stats, long long n) {
+  const int b = blockIdx.y;
+  const float* p = y + static_cast<long long>(b) * n;
+  float s = 0.f, ss = 0.f;
+  for (long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x * 4) {
+    const float4 v = ld4(p + i);
+    s += (v.x + v.y) + (v.z + v.w);
+    ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  __shared__ float red[2][8];
+  s = warp_sum(s);
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = ss;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0, c = 0;
+    for (int i = 0; i < 8; ++i) {
+      a += red[0][i];
+      c += red[1][i];
+    }
+    atomicAdd(&stats[2 * b], a);
+    atomicAdd(&stats[2 * b + 1], c);
+  }
+}
+
+__global__ void __launch_bounds__(256) gn_mod_silu_kernel(const float* __restrict__ y, const double* __restrict__ stats,
+                                                          const float* __restrict__ gn_w, const float* __restrict__ gn_b,
+                                                          const float* __restrict__ emb, float* __restrict__ a, int B, int npix, int C) {
+  const long long total = static_cast<long long>(B) * npix * C;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const int b = static_cast<int>(i / (static_cast<long long>(npix) * C));
+  const double cnt = static_cast<double>(npix) * C;
+  const double mean = stats[2 * b] / cnt;
+  const double var = stats[2 * b + 1] / cnt - mean * mean;
+  const float rstd = rsqrtf(static_cast<float>(var > 0 ? var : 0) + 1e-6f);
+  const float shift = emb[b * 2 * C + c], scale = emb[b * 2 * C + C + c];
+  float v = (y[i] - static_cast<float>(mean)) * rstd * gn_w[c] + gn_b[c];
+  v = v * (1.f + scale) + shift;
+  a[i] = silu_f(v);
+}
+
+constexpr int kC2Pix = 8;
+__global__ void conv3x3_s2_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ y, int g, int C) {
+  extern __shared__ float in_s[];  // [3][2*kC2Pix+1][C]
+  const int go = g / 2;
+  const int b = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * kC2Pix;
+  const int cols = 2 * kC2Pix + 1;
+  for (int i = threadIdx.x; i < 3 * cols * C; i += blockDim.x) {
+    const int c = i % C, col = (i / C) % cols, ky = i / (C * cols);
+    const int iy = 2 * oy + ky - 1, ix = 2 * ox0 + col - 1;
+    in_s[i] = (iy >= 0 && iy < g && ix >= 0 && ix < g) ? a[((static_cast<long long>(b) * g + iy) * g + ix) * C + c] : 0.f;
+  }
+  __syncthreads();
+  const int oc = threadIdx.x;
+  float acc[kC2Pix];
+#pragma unroll
+  for (int p = 0; p < kC2Pix; ++p) acc[p] = bias[oc];
+  for (int tap = 0; tap < 9; ++tap) {
+    const int ky = tap / 3, kx = tap % 3;
+    const float* wp = w + static_cast<long long>(tap) * C * C + oc;
+    const float* ip = in_s + (ky * cols + kx) * C;
+    for (int c = 0; c < C; ++c) {
+      const float wv = wp[static_cast<long long>(c) * C];
+#pragma unroll
+      for (int p = 0; p < kC2Pix; ++p) acc[p] = fmaf(wv, ip[2 * p * C + c], acc[p]);
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < kC2Pix; ++p)
+    if (ox0 + p < go) y[((static_cast<long long>(b) * go + oy) * go + ox0 + p) * C + oc] = acc[p];
+}
+
+__global__ void tpm_tail_kernel(const float* __restrict__ y2, int go, int C, const float* __restrict__ fc1_w,
+                                const float* __restrict__ fc1_b, const float* __restrict__ fc2_w, const float* __restrict__ fc2_b,
+                                float eps, float* __restrict__ alpha_beta) {
+  __shared__ float pooled[128];
+  __shared__ float hid[128];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const float* p = y2 + static_cast<long long>(b) * go * go * C;
+  if (t < C) {
+    float mx = -INFINITY;
+    for (int i = 0; i < 16; ++i) {
+      const int r0 = (i * go) / 16, r1 = ((i + 1) * go + 15) / 16;
+      for (int j = 0; j < 16; ++j) {
+        const int c0 = (j * go) / 16, c1 = ((j + 1) * go + 15) / 16;
+        float s = 0.f;
+        for (int r = r0; r < r1; ++r)
+          for (int c = c0; c < c1; ++c) s += p[(static_cast<long long>(r) * go + c) * C + t];
+        mx = fmaxf(mx, s / static_cast<float>((r1 - r0) * (c1 - c0)));
+      }
+    }
+    pooled[t] = mx;
+  }
+  __syncthreads();
+  if (t < 128) {
+    float acc = fc1_b[t];
+    for (int c = 0; c < C; ++c) acc = fmaf(fc1_w[t * C + c], pooled[c], acc);
+    hid[t] = silu_f(acc);
+  }
+  __syncthreads();
+  if (t < 2) {
+    float acc = fc2_b[t];
+    for (int j = 0; j < 128; ++j) acc = fmaf(fc2_w[t * 128 + j], hid[j], acc);
+    alpha_beta[b * 2 + t] = expf(acc) + eps;
+  }
+}
+
+// schedule update (modeling_sd3_pnt.py:557-590, 608)
+__global__ void schedule_kernel(const ScheduleArgs a) {
+  const int i = threadIdx.x;
+  int done = 1;
+  if (i < a.B) {
+    const float p1 = a.alpha_beta[2 * i], p2 = a.alpha_beta[2 * i + 1];
+    float alpha, beta;
+    if (a.prediction_type == 0) {
+      alpha = p1;
+      beta = p2;
+    } else {
+      alpha = p1 * (p2 - 2.f) + 1.f;
+      beta = (1.f - p1) * (p2 - 2.f) + 1.f;
+    }
+    const float sigma = a.sigma_hist[i * (a.T + 1) + a.step];
+    float ratio = a.predict ? (alpha - 1.f) / (alpha + beta - 2.f) : a.ratios[i * a.T + a.step];
+    float sigma_next;
+    if (a.relative) {
+      ratio = fminf(fmaxf(ratio, a.epsilon), 1.f - a.epsilon);
+      sigma_next = sigma * ratio;
+    } else {
+      ratio = fminf(fmaxf(ratio, a.epsilon), sigma);
+      ratio = fminf(fmaxf(ratio, 0.f), 1.f - a.epsilon);
+      sigma_next = sigma - ratio;
+    }
+    const double A = alpha, Bq = beta, r = ratio;
+    const double lp = (A - 1.0) * log(r) + (Bq - 1.0) * log1p(-r) + lgamma(A + Bq) - lgamma(A) - lgamma(Bq);
+    int mask = 0;
+    if (sigma < a.min_sigma) {
+      mask = 1;
+      if (a.predict) sigma_next = 0.f;
+    }
+    const int o = i * a.T + a.step;
+    a.alphas[o] = alpha;
+    a.betas[o] = beta;
+    a.logprobs[o] = static_cast<float>(lp);
+    a.masks[o] = mask;
+    a.sigma_hist[i * (a.T + 1) + a.step + 1] = sigma_next;
+    done = sigma_next < a.min_sigma ? 1 : 0;
+  }
+  const int all = __syncthreads_and(done);
+  if (i == 0) a.all_done[a.step] = all;
+}
+
+inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------------------
+int k_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
+  if (n <= 0) return 0;
+  long long blocks = (n / 4 + 255) / 256;
+  blocks = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
+  cast_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(in, out, n);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_timestep_embedding(const float* timestep, int t_stride, float scale, float* out, int Bt, int rep, cudaStream_t s) {
+  timestep_embedding_kernel<<<Bt, 128, 0, s>>>(timestep, t_stride, scale, out, Bt, rep);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_gemv_f32(const float* W, const float* bias, const float* x, int ldx, const float* addend, float* y, int ldy, int Bt, int J, int K,
+               int act, cudaStream_t s) {
+  return gemv_launch<float>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act, s);
+}
+int k_gemv_bf16(const bf16* W, const float* bias, const float* x, int ldx, const float* addend, float* y, int ldy, int Bt, int J, int K,
+                int act, cudaStream_t s) {
+  return gemv_launch<bf16>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act, s);
+}
+
+int k_patchify(const float* latents, const float* Wp, const float* bias, const float* pos_table, int pos_max, float* x, int Bl, int dup,
+               int C, int Hl, int Wl, int D, float* h1_out, bf16* tpm_x, cudaStream_t s) {
+  const int N = (Hl / 2) * (Wl / 2);
+  TPDM_CHECK(C * 4 == 64, TPDM_ERR_SHAPE, "patchify: in_channels*patch^2 must be 64 (got %d)", C * 4);
+  TPDM_CHECK(N % kPatchTok == 0, TPDM_ERR_SHAPE, "patchify: token count %d must be a multiple of %d", N, kPatchTok);
+  TPDM_CHECK(Hl / 2 <= pos_max && Wl / 2 <= pos_max, TPDM_ERR_SHAPE, "patchify: grid %dx%d exceeds pos_embed_max_size %d", Hl / 2,
+             Wl / 2, pos_max);
+  dim3 grid(N / kPatchTok, Bl);
+  patchify_kernel<<<grid, 256, kPatchTok * 64 * sizeof(float), s>>>(latents, Wp, bias, pos_table, pos_max, x, Bl, dup, C, Hl, Wl, D,
+                                                                   h1_out, tpm_x);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_ln_modulate(const LnSeg* segs, int nseg, int D, cudaStream_t s) {
+  TPDM_CHECK(nseg >= 1 && nseg <= 2 && D % 4 == 0, TPDM_ERR_ARG, "ln_modulate: bad arguments");
+  LnParams P;
+  P.nseg = nseg;
+  P.D = D;
+  P.seg[0] = segs[0];
+  P.seg[1] = nseg > 1 ? segs[1] : segs[0];
+  P.rows0 = static_cast<long long>(segs[0].rows) * segs[0].batch;
+  P.rows_total = P.rows0 + (nseg > 1 ? static_cast<long long>(segs[1].rows) * segs[1].batch : 0);
+  ln_modulate_kernel<<<blocks_for(P.rows_total, 8), 256, 0, s>>>(P);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_norm_out(const float* x, bf16* xn, const float* shift, const float* scale, int mod_stride, int B, int cfg_pairs, int N, int D,
+               int g, float guidance, bf16* tpm_x, float* h2_out, cudaStream_t s) {
+  norm_out_kernel<<<blocks_for(static_cast<long long>(B) * N, 8), 256, 0, s>>>(x, xn, shift, scale, mod_stride, B, cfg_pairs, N, D, g,
+                                                                               guidance, tpm_x, h2_out);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_qk_rmsnorm(bf16* qkv, int Bt, int S, int row0, int rows, int H, int dp, int d, const float* wq, const float* wk, cudaStream_t s) {
+  const long long total = static_cast<long long>(Bt) * rows * 2 * H;
+  qk_rmsnorm_kernel<<<blocks_for(total, 8), 256, 0, s>>>(qkv, Bt, S, row0, rows, H, dp, d, wq, wk);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_unpatchify(const float* pout, int B, int cfg_pairs, float guidance, int C, int Hl, int Wl, float* velocity, float* latents,
+                 const float* sigma, const float* sigma_next, int sigma_stride, float* history, cudaStream_t s) {
+  const long long total = static_cast<long long>(B) * C * Hl * Wl;
+  unpatchify_kernel<<<blocks_for(total, 256), 256, 0, s>>>(pout, B, cfg_pairs, guidance, C, Hl, Wl, velocity, latents, sigma, sigma_next,
+                                                          sigma_stride, history);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_euler(const float* v, const float* sigma_next, const float* sigma, const float* sample, float* prev, int B, long long n,
+            cudaStream_t s) {
+  euler_kernel<<<blocks_for(static_cast<long long>(B) * n, 256), 256, 0, s>>>(v, sigma_next, sigma, sample, prev, B, n);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_cfg_combine(const float* in, float* out, float* out2, int B, int n, float guidance, cudaStream_t s) {
+  cfg_combine_kernel<<<blocks_for(static_cast<long long>(B) * n, 256), 256, 0, s>>>(in, out, out2, B, n, guidance);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_nchw_to_nhwc_bf16(const float* x, bf16* out, int B, int C, int g, cudaStream_t s) {
+  dim3 grid((g * g + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  nchw_to_nhwc_bf16_kernel<<<grid, block, 0, s>>>(x, out, B, C, g);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_gn_stats(const float* y, double* stats, int B, long long n, cudaStream_t s) {
+  TPDM_CHECK(n % 4 == 0, TPDM_ERR_SHAPE, "gn_stats: n must be a multiple of 4");
+  dim3 grid(64, B);
+  gn_stats_kernel<<<grid, 256, 0, s>>>(y, stats, n);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_gn_mod_silu(const float* y, const double* stats, const float* gn_w, const float* gn_b, const float* emb, float* a, int B, int npix,
+                  int C, cudaStream_t s) {
+  gn_mod_silu_kernel<<<blocks_for(static_cast<long long>(B) * npix * C, 256), 256, 0, s>>>(y, stats, gn_w, gn_b, emb, a, B, npix, C);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_conv3x3_s2(const float* a, const float* w, const float* bias, float* y, int B, int g, int C, cudaStream_t s) {
+  TPDM_CHECK(C <= 1024 && g % 2 == 0, TPDM_ERR_SHAPE, "conv3x3_s2: unsupported shape");
+  const int go = g / 2;
+  dim3 grid((go + kC2Pix - 1) / kC2Pix, go, B);
+  const size_t smem = static_cast<size_t>(3) * (2 * kC2Pix + 1) * C * sizeof(float);
+  conv3x3_s2_kernel<<<grid, C, smem, s>>>(a, w, bias, y, g, C);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_tpm_tail(const float* y2, int B, int go, int C, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b,
+               float eps, float* alpha_beta, cudaStream_t s) {
+  TPDM_CHECK(C <= 128, TPDM_ERR_SHAPE, "tpm_tail: conv_out_channels %d > 128", C);
+  tpm_tail_kernel<<<B, 128, 0, s>>>(y2, go, C, fc1_w, fc1_b, fc2_w, fc2_b, eps, alpha_beta);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_schedule(const ScheduleArgs& a, cudaStream_t s) {
+  TPDM_CHECK(a.B <= 1024, TPDM_ERR_SHAPE, "schedule: batch %d > 1024", a.B);
+  TPDM_CHECK(a.predict || a.ratios, TPDM_ERR_ARG, "schedule: predict == 0 needs injected ratios");
+  const int threads = ((a.B + 31) / 32) * 32;
+  schedule_kernel<<<1, threads, 0, s>>>(a);
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace tpdm

@@ -99,9 +99,9 @@ typedef struct tpdm_weights {
   const float* adaln_b;   /* [R] */
   const void* proj_w;     /* bf16 [4*out_channels][D]  proj_out */
   const float* proj_b;
-  const tpdm_block_weights* blocks; /* HOST array [num_layers] */
+  const tpdm_block_weights* blocks; /* HOST array [num_layers]; null = no MMDiT (TimePredictor-only ctx) */
   /* TimePredictor (modeling_sd3_pnt.py:85-126) */
-  const void* tpm_conv1_w;    /* bf16 [C1][9][2D]  conv1.weight permuted (oc, ky*3+kx, c) */
+  const void* tpm_conv1_w;    /* bf16 [C1][9][2D]  conv1.weight permuted (oc, ky*3+kx, c); null = no TimePredictor */
   const float* tpm_conv1_b;   /* [C1] */
   const float* tpm_lin_w;     /* [2*C1][D]  norm1.linear */
   const float* tpm_lin_b;
@@ -142,7 +142,8 @@ int tpdm_mmdit_forward(tpdm_plan* plan, const float* latents, const float* times
                        const float* pooled, float* out_sample, float* out_temb, float* out_h1, float* out_h2,
                        void* stream);
 
-/* TimePredictor.forward (modeling_sd3_pnt.py:100-115) on NCHW input x [batch][2D][g][g], temb [batch][D] -> [batch][2]. */
+/* TimePredictor.forward (modeling_sd3_pnt.py:100-115) on NCHW input x [Bt][2D][g][g], temb [Bt][D] -> [Bt][2]
+ * (Bt = the plan's transformer batch). */
 int tpdm_tpm_forward(tpdm_plan* plan, const float* x_nchw, const float* temb, float* out_alpha_beta, void* stream);
 
 /* CustomFlowMatchEulerDiscreteScheduler.custom_step (src/models/model_utilis.py:52-74):
@@ -152,10 +153,12 @@ int tpdm_euler_step(const float* model_output, const float* sigma_next, const fl
 
 /* The adaptive loop, SD3PredictNextTimeStepModel.forward (modeling_sd3_pnt.py:504-612).
  * begin: latents [batch][C][h][w]; embeddings for the negative and positive prompt [batch][T][J], [batch][pooled].
- *        ratios: optional [batch][max_steps] injected Beta draws (predict == 0); null -> Beta mode (predict == 1). */
+ *        predict != 0: ratio = Beta(alpha, beta).mode (:567).  predict == 0: ratio = ratios[b][step] when `ratios`
+ *        ([batch][max_steps], injected draws) is given, else a device-side Beta(alpha, beta) draw (Philox stream
+ *        (seed, sample b, step), Marsaglia-Tsang gammas) standing in for beta_dist.sample() (:569). */
 int tpdm_sample_begin(tpdm_plan* plan, const float* latents, const float* neg_embeds, const float* pos_embeds,
                       const float* neg_pooled, const float* pos_pooled, float guidance_scale, int predict,
-                      const float* ratios, void* stream);
+                      const float* ratios, unsigned long long seed, void* stream);
 /* one denoising step `step` (0-based): MMDiT -> CFG -> TPM -> schedule update -> Euler.  No host synchronisation. */
 int tpdm_sample_step(tpdm_plan* plan, int step, void* stream);
 /* device-resident results; all [batch][max_steps] row-major unless stated */
@@ -173,6 +176,14 @@ typedef struct tpdm_sample_state {
   float* history_latents;/* [max_steps][batch][C][h][w] */
 } tpdm_sample_state;
 int tpdm_sample_state_get(tpdm_plan* plan, tpdm_sample_state* out);
+
+/* ---- measurement hooks used by bench.py -------------------------------------------------------------------------- */
+/* kernels launched by this library in this process since the last reset */
+long long tpdm_launch_count(int reset);
+/* bracket every GEMM (class 0) and attention (class 1) launch with CUDA events on the launching stream until stop;
+ * stop returns, per class, the summed device time (ms), the algorithmic FLOPs and the number of launches */
+int tpdm_profile_start(int max_records);
+int tpdm_profile_stop(double* ms, double* flops, long long* count, int n_classes);
 
 /* ---- unit entry points used by tests/ (one kernel each) ---------------------------------------------------------- */
 /* out = epilogue(A[batch][rows][K] (bf16) . W[N][K]^T (bf16)); epi: 0 bias->bf16, 1 bias->f32, 2 bias+gelu->bf16,

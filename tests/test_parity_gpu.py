@@ -1,0 +1,301 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C-ABI against the fp32 oracle and the golden
+fixtures.  Tolerances are BASELINE.json's: per-step velocity <= 2e-2 rel-L2, sigma sequence <= 1e-3 abs, final latent
+<= 3e-2 rel-L2 (bf16 tensor-core path vs fp32 oracle)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+VEL_TOL, SIGMA_TOL, LATENT_TOL = 2e-2, 1e-3, 3e-2
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from tpdm_b200 import _lib
+
+    _lib.load()
+    return _lib
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# unit kernels through the C-ABI
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch,rows,N,K,epi", [
+    (1, 128, 256, 64, 1), (2, 333, 384, 384, 0), (2, 333, 1152, 384, 2), (2, 256, 384, 1536, 3), (2, 256, 64, 384, 1),
+    (1, 1, 8, 64, 1), (3, 130, 200, 72, 0), (2, 1024, 4608, 1536, 0), (2, 1024, 1536, 6144, 3)])
+def test_gemm(L, batch, rows, N, K, epi):
+    torch.manual_seed(0)
+    lib = L.load()
+    dev = "cuda"
+    A = (torch.randn(batch, rows, K, device=dev) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+    bias, gate = torch.randn(N, device=dev), torch.randn(batch, N, device=dev)
+    acc = A.float() @ W.float().t() + bias
+    if epi in (0, 2):
+        out = torch.zeros(batch, rows, N, device=dev, dtype=torch.bfloat16)
+        ref = acc if epi == 0 else torch.nn.functional.gelu(acc, approximate="tanh")
+        tol = 6e-3
+    elif epi == 1:
+        out, ref, tol = torch.zeros(batch, rows, N, device=dev), acc, 1e-4
+    else:
+        out = torch.randn(batch, rows, N, device=dev)
+        ref, tol = out + gate[:, None, :] * acc, 1e-4
+    L.check(lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gate), L.ptr(out), batch, rows, N, K, epi, None))
+    torch.cuda.synchronize()
+    assert rel(out, ref) < tol
+
+
+def test_gemm_rejects_bad_arguments(L):
+    lib = L.load()
+    A = torch.zeros(1, 8, 60, device="cuda", dtype=torch.bfloat16)
+    W = torch.zeros(8, 60, device="cuda", dtype=torch.bfloat16)
+    out = torch.zeros(1, 8, 8, device="cuda")
+    with pytest.raises(ValueError):
+        L.check(lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), None, None, L.ptr(out), 1, 8, 8, 60, 1, None))   # K % 8 != 0
+    with pytest.raises(ValueError):
+        L.check(lib.tpdm_gemm_bf16(None, L.ptr(W), None, None, L.ptr(out), 1, 8, 8, 64, 1, None))
+    with pytest.raises(ValueError):
+        L.check(lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), None, None, L.ptr(out), 1, 8, 8, 64, 3, None))   # gate missing
+
+
+@pytest.mark.parametrize("Bt,S,H,d,q_rows", [(1, 128, 1, 64, 0), (1, 1, 1, 64, 0), (2, 589, 4, 96, 0), (1, 1357, 4, 64, 0),
+                                             (1, 1357, 4, 64, 1024), (2, 300, 3, 32, 0), (1, 4429, 2, 64, 0)])
+def test_joint_attention(L, Bt, S, H, d, q_rows):
+    torch.manual_seed(1)
+    lib = L.load()
+    dp = 64 if d <= 64 else 128
+    qkv = torch.zeros(Bt, S, 3, H, dp, device="cuda")
+    qkv[..., :d] = torch.randn(Bt, S, 3, H, d, device="cuda") * 1.5
+    qkv = qkv.bfloat16().contiguous()
+    out = torch.zeros(Bt, S, H, dp, device="cuda", dtype=torch.bfloat16)
+    q, k, v = (qkv[:, :, i, :, :d].float().transpose(1, 2) for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2)
+    L.check(lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, dp, d, q_rows, None))
+    torch.cuda.synchronize()
+    rows = q_rows or S
+    assert rel(out[:, :rows, :, :d], ref[:, :rows]) < 6e-3
+    if dp > d:
+        assert float(out[..., d:].float().abs().max()) == 0.0
+
+
+def test_attention_large_logits_trigger_rescale(L):
+    """Rows whose running max grows by more than 2^8 between KV tiles exercise the lazy O-rescale path."""
+    torch.manual_seed(2)
+    lib = L.load()
+    Bt, S, H, d = 1, 512, 2, 64
+    qkv = torch.randn(Bt, S, 3, H, d, device="cuda")
+    qkv[:, :, 0] *= 6.0
+    qkv[:, 300:, 1] *= 6.0     # later key tiles carry much larger logits
+    qkv = qkv.bfloat16().contiguous()
+    out = torch.zeros(Bt, S, H, d, device="cuda", dtype=torch.bfloat16)
+    q, k, v = (qkv[:, :, i].float().transpose(1, 2) for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2)
+    L.check(lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, 64, d, 0, None))
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,g,C,N", [(2, 16, 128, 128), (1, 64, 3072, 128), (1, 8, 64, 128), (1, 128, 128, 128)])
+def test_conv3x3_implicit_gemm(L, B, g, C, N):
+    torch.manual_seed(3)
+    lib = L.load()
+    x = torch.randn(B, C, g, g, device="cuda").bfloat16()
+    w = (torch.randn(N, C, 3, 3, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(B, g * g, N)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    wp = w.permute(0, 2, 3, 1).reshape(N, 9 * C).contiguous()
+    out = torch.zeros(B, g * g, N, device="cuda")
+    L.check(lib.tpdm_conv3x3_nhwc(L.ptr(xn), L.ptr(wp), L.ptr(bias), L.ptr(out), B, g, C, N, None))
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 1e-4
+
+
+def test_ln_modulate(L):
+    torch.manual_seed(4)
+    lib = L.load()
+    B, rows, D = 2, 333, 1536
+    x = torch.randn(B, rows, D, device="cuda") * 3 + 1
+    mod = torch.randn(B, 4 * D, device="cuda")
+    out = torch.zeros(B, rows, D, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.tpdm_ln_modulate(L.ptr(x), mod.data_ptr(), mod.data_ptr() + 4 * D, 4 * D, L.ptr(out), B, rows, D, None))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + mod[:, None, D:2 * D]) + mod[:, None, :D]
+    assert rel(out, ref) < 4e-3
+
+
+def test_euler_step_matches_reference_fixture(golden):
+    from tpdm_b200.model_utilis import CustomFlowMatchEulerDiscreteScheduler
+
+    fx = golden("pieces_ref")
+    sch = CustomFlowMatchEulerDiscreteScheduler()
+    prev = sch.custom_step(fx["euler.model_output"].cuda(), fx["euler.sigma_next"].cuda(), fx["euler.sigma"].cuda(),
+                           fx["euler.sample"].cuda(), return_dict=False)[0]
+    assert torch.allclose(prev.cpu(), fx["euler.prev"], atol=1e-6)   # fp32 fma vs mul+add
+    assert sch.custom_step(fx["euler.model_output"].cuda(), fx["euler.sigma_next"].cuda(), fx["euler.sigma"].cuda(),
+                           fx["euler.sample"].cuda()).prev_sample.shape == prev.shape
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# TimePredictor against the reference's own outputs
+# ---------------------------------------------------------------------------------------------------------------
+def test_time_predictor_matches_reference_fixture(golden):
+    from tpdm_b200.modeling_sd3_pnt import TimePredictor
+
+    fx = golden("tpm_ref")
+    tp = TimePredictor(128, 128).cuda()
+    tp.load_state_dict({k: v for k, v in fx.items() if not k.startswith("grad.") and k not in ("x", "temb", "alpha_beta")})
+    y = tp(fx["x"].cuda(), fx["temb"].cuda())
+    assert y.shape == (2, 2)
+    assert torch.allclose(y.cpu(), fx["alpha_beta"], rtol=3e-3), (y.cpu(), fx["alpha_beta"])
+
+
+def test_time_predictor_sd3m_shape_vs_oracle():
+    from oracle import sd3_oracle as O
+    from tpdm_b200.modeling_sd3_pnt import TimePredictor
+
+    torch.manual_seed(5)
+    ora = O.OracleTimePredictor(128, 3072).cuda()
+    with torch.no_grad():   # make the head input-sensitive (the default init is bias dominated)
+        ora.fc2.weight.mul_(20)
+        ora.fc1.weight.mul_(5)
+    tp = TimePredictor(128, 3072).cuda()
+    tp.load_state_dict(ora.state_dict())
+    x = torch.randn(1, 3072, 64, 64, device="cuda")
+    temb = torch.randn(1, 1536, device="cuda")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        ref = ora(x, temb)
+    got = tp(x, temb)
+    assert torch.allclose(got, ref, rtol=5e-3), (got, ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MMDiT forward and the adaptive loop, tiny config (BASELINE.json configs[0])
+# ---------------------------------------------------------------------------------------------------------------
+def _tiny(qk_norm=None):
+    from oracle import sd3_oracle as O
+    from tpdm_b200.modeling_sd3_pnt import SD3PredictNextTimeStepModel
+
+    cfg = O.tiny_config(qk_norm=qk_norm)
+    pipe = O.build_pipeline(cfg)
+    inp = O.synthetic_inputs(cfg, batch=2)
+    tcfg = dict(sample_size=32, num_layers=2, attention_head_dim=96, num_attention_heads=4, caption_projection_dim=384,
+                pos_embed_max_size=96, qk_norm=qk_norm)
+    model = SD3PredictNextTimeStepModel(transformer_config=tcfg, torch_dtype=torch.float32, device="cuda")
+    model.transformer.load_state_dict(pipe.transformer.state_dict())
+    model.time_predictor.load_state_dict(pipe.time_predictor.state_dict())
+    return pipe, inp, model
+
+
+def test_mmdit_forward_tiny_vs_golden(golden):
+    pipe, inp, model = _tiny()
+    fx = golden("tiny_block")
+    lat2 = torch.cat([inp["latents"]] * 2).cuda()
+    pe = torch.cat([inp["negative_prompt_embeds"], inp["prompt_embeds"]]).cuda()
+    pp = torch.cat([inp["negative_pooled_prompt_embeds"], inp["pooled_prompt_embeds"]]).cuda()
+    v, temb, h1, h2 = model.transformer(lat2, pe, pp, fx["timestep"].cuda(), return_dict=False)
+    assert v.shape == (4, 16, 32, 32) and temb.shape == (4, 384) and h1.shape == (4, 256, 384) and h2.shape == (4, 256, 384)
+    assert rel(temb, fx["temb"]) < 1e-4
+    assert rel(h1[:, 0], fx["h1_row0"]) < 1e-5
+    assert rel(h2[:, 17], fx["h2_tok17"]) < VEL_TOL
+    assert rel(v, fx["velocity"]) < VEL_TOL
+    out = model.transformer(lat2, pe, pp, fx["timestep"].cuda())
+    assert torch.equal(out.sample, v) and torch.equal(out["hidden_states_2"], h2)
+
+
+@pytest.mark.parametrize("qk_norm", [None, "rms_norm"])
+def test_tiny_trajectory_vs_golden(golden, qk_norm):
+    pipe, inp, model = _tiny(qk_norm)
+    fx = golden("tiny_traj" if qk_norm is None else "tiny_traj_qknorm")
+    cu = {k: v.cuda() for k, v in inp.items()}
+    out = model(**cu, max_inference_steps=8, guidance_scale=7.0, predict=True, return_velocities=True)
+    T = fx["sigmas"].shape[1]
+    assert out.sigmas.shape == (2, T)
+    assert float((out.sigmas.cpu() - fx["sigmas"]).abs().max()) < SIGMA_TOL
+    assert torch.equal(out.prob_masks.cpu().to(torch.uint8), fx["prob_masks"])
+    assert float((out.alphas.cpu() - fx["alphas"]).abs().max()) < 2e-2
+    assert float((out.logprobs.cpu() - fx["logprobs"]).abs().max()) < 5e-3
+    for t in range(T):
+        assert rel(out["velocities"][:, t], fx["velocities"][:, t]) < VEL_TOL, t
+    assert rel(out.latents, fx["final_latents"]) < LATENT_TOL
+    assert [int(i) for i in out.last_valid_indices] == fx["last_valid_indices"].tolist()
+    assert rel(out.tembs, fx["tembs"]) < 1e-3
+    assert out.hidden_states_combineds is None and out.images == []
+
+
+def test_tiny_injected_ratios_vs_golden(golden):
+    pipe, inp, model = _tiny()
+    fx = golden("tiny_traj")
+    cu = {k: v.cuda() for k, v in inp.items()}
+    out = model(**cu, max_inference_steps=8, predict=False, ratios=fx["sample.ratios"])
+    assert float((out.sigmas.cpu() - fx["sample.sigmas"]).abs().max()) < 1e-5       # sigma_next = sigma * injected ratio
+    assert float((out.logprobs.cpu() - fx["sample.logprobs"]).abs().max()) < 2e-2
+    assert rel(out.latents, fx["sample.final_latents"]) < LATENT_TOL
+    # replay (only_predict_logprobs) reproduces the rollout log-probs from the recorded TPM inputs
+    assert out.hidden_states_combineds.shape == (2, 8, 768, 16, 16)
+    lp = model.only_predict_logprobs(out.sigmas, out.hidden_states_combineds, out.tembs)["logprobs"]
+    assert float((lp - out.logprobs).abs().max()) < 2e-3
+    with pytest.raises(ValueError):
+        model.only_predict_logprobs(None, None, None)
+
+
+def test_tiny_early_termination_and_device_sampler():
+    """min_sigma high enough that the batch finishes before max steps: loop must stop exactly like the reference
+    (one masked step after sigma < min_sigma) and device-side Beta draws must be valid and seed-reproducible."""
+    pipe, inp, model = _tiny()
+    model.min_sigma = 0.2
+    pipe.min_sigma = 0.2
+    cu = {k: v.cuda() for k, v in inp.items()}
+    ref = pipe(**inp, max_inference_steps=28, predict=True)
+    out = model(**cu, max_inference_steps=28, predict=True)
+    assert out.sigmas.shape == ref["sigmas"].shape
+    assert float((out.sigmas.cpu() - ref["sigmas"]).abs().max()) < SIGMA_TOL
+    assert torch.equal(out.prob_masks.cpu(), ref["prob_masks"])
+    assert rel(out.latents, ref["final_latents"]) < LATENT_TOL
+    g = torch.Generator().manual_seed(3)
+    a = model(**cu, max_inference_steps=6, predict=False, generator=g)
+    b = model(**cu, max_inference_steps=6, predict=False, generator=torch.Generator().manual_seed(3))
+    assert torch.equal(a.sigmas, b.sigmas)
+    r = a.sigmas[:, 0]
+    assert bool(((r > 0) & (r < 1)).all()) and float(a.sigmas.std()) > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SD3-medium shapes (BASELINE.json configs[1]): one MMDiT forward vs the fp32 oracle on the GPU (TF32 off)
+# ---------------------------------------------------------------------------------------------------------------
+def test_mmdit_forward_sd3_medium_1024_vs_oracle():
+    from oracle import sd3_oracle as O
+    from tpdm_b200.transformer_sd3 import CustomSD3Transformer2DModel
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.sd3_medium_config()
+    torch.manual_seed(1234)
+    with torch.device("cuda"):
+        ora = O.OracleSD3Transformer(cfg).requires_grad_(False).eval()
+    ora = ora.to("cuda")    # the sincos buffer is built with numpy on the host
+    model =CustomSD3Transformer2DModel(sample_size=128, num_layers=24, attention_head_dim=64, num_attention_heads=24,
+                                        caption_projection_dim=1536, pos_embed_max_size=192, device="cuda", dtype=torch.bfloat16)
+    model.load_state_dict(ora.state_dict())
+    ora.load_state_dict(model.state_dict())     # both sides see the same bf16-representable weights
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lat = torch.randn(1, 16, 128, 128, device="cuda", generator=g).repeat(2, 1, 1, 1)
+    enc = torch.randn(2, 333, 4096, device="cuda", generator=g)
+    pooled = torch.randn(2, 2048, device="cuda", generator=g)
+    ts = torch.tensor([700.0, 700.0], device="cuda")
+    with torch.no_grad():
+        rv, rt, rh1, rh2 = ora(lat, enc, pooled, ts)
+    v, temb, h1, h2 = model(lat.float(), enc, pooled, ts, return_dict=False)
+    assert rel(temb, rt) < 2e-3
+    assert rel(h1, rh1) < 1e-3
+    assert rel(h2, rh2) < VEL_TOL
+    assert rel(v, rv) < VEL_TOL

@@ -56,9 +56,12 @@ EXPORTS = {
     "tpdm_mmdit_forward": (C.c_int, [vp] + [vp] * 8 + [vp]),
     "tpdm_tpm_forward": (C.c_int, [vp, vp, vp, vp, vp]),
     "tpdm_euler_step": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_longlong, vp]),
-    "tpdm_sample_begin": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, vp, vp]),
+    "tpdm_sample_begin": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, vp, C.c_ulonglong, vp]),
     "tpdm_sample_step": (C.c_int, [vp, C.c_int, vp]),
     "tpdm_sample_state_get": (C.c_int, [vp, C.POINTER(TpdmSampleState)]),
+    "tpdm_launch_count": (C.c_longlong, [C.c_int]),
+    "tpdm_profile_start": (C.c_int, [C.c_int]),
+    "tpdm_profile_stop": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "tpdm_gemm_bf16": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tpdm_joint_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tpdm_conv3x3_nhwc": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),

@@ -16,7 +16,7 @@ struct tpdm_ctx {
   tpdm_config cfg;
   tpdm_weights w;
   std::vector<tpdm_block_weights> blocks;
-  bool has_weights = false;
+  bool has_weights = false, has_mmdit = false, has_tpm = false;
   int D = 0, dp = 0, Dp = 0, R = 0, device = 0;
 };
 
@@ -58,6 +58,7 @@ struct tpdm_plan {
   int *masks, *all_done;
   float guidance = 7.0f;
   int predict = 1, begun = 0, have_ratios = 0;
+  unsigned long long seed = 0;
   std::vector<BlockOps> blk;
   GemmOp ctx_embed, proj_out, conv1;
 };
@@ -124,6 +125,10 @@ int build_ops(tpdm_plan* p) {
   const int D = ctx->D, Dp = ctx->Dp, R = ctx->R, L = ctx->cfg.num_layers;
   const int Bt = p->Bt, N = p->N, T = p->T, S = p->S;
   const tpdm_weights& w = ctx->w;
+  if (ctx->has_tpm)
+    TPDM_TRY(gemm_op_init_conv3x3(&p->conv1, p->tpm_x, Bt, p->g, 2 * D, w.tpm_conv1_w, ctx->cfg.tpm_channels, EPI_BIAS_F32, p->y1,
+                                  ctx->cfg.tpm_channels, w.tpm_conv1_b));
+  if (!ctx->has_mmdit) return 0;
   p->blk.resize(L);
   for (int i = 0; i < L; ++i) {
     const tpdm_block_weights& bw = ctx->blocks[i];
@@ -162,8 +167,6 @@ int build_ops(tpdm_plan* p) {
   const int PO = 4 * ctx->cfg.out_channels;
   TPDM_TRY(gemm_op_init(&p->proj_out, p->xn_img, D, static_cast<long long>(N) * D, N, Bt, D, w.proj_w, PO, EPI_BIAS_F32, p->pout,
                         static_cast<long long>(N) * PO, PO, w.proj_b, nullptr, 0));
-  TPDM_TRY(gemm_op_init_conv3x3(&p->conv1, p->tpm_x, Bt, p->g, 2 * D, w.tpm_conv1_w, ctx->cfg.tpm_channels, EPI_BIAS_F32, p->y1,
-                                ctx->cfg.tpm_channels, w.tpm_conv1_b));
   return 0;
 }
 
@@ -289,19 +292,29 @@ int tpdm_destroy(tpdm_ctx* ctx) {
 }
 
 int tpdm_set_weights(tpdm_ctx* ctx, const tpdm_weights* w) {
-  TPDM_CHECK(ctx && w && w->blocks, TPDM_ERR_ARG, "tpdm_set_weights: null argument");
+  TPDM_CHECK(ctx && w, TPDM_ERR_ARG, "tpdm_set_weights: null argument");
   ctx->w = *w;
-  ctx->blocks.assign(w->blocks, w->blocks + ctx->cfg.num_layers);
-  ctx->w.blocks = ctx->blocks.data();
-  const void* req[] = {w->patch_w, w->patch_b, w->pos_table, w->t_w1, w->t_b1, w->t_w2, w->t_b2, w->p_w1, w->p_b1, w->p_w2, w->p_b2,
-                       w->ctx_w, w->ctx_b, w->adaln_w, w->adaln_b, w->proj_w, w->proj_b};
-  for (const void* p : req) TPDM_CHECK(p != nullptr, TPDM_ERR_ARG, "tpdm_set_weights: a required MMDiT weight pointer is null");
-  for (int i = 0; i < ctx->cfg.num_layers; ++i) {
-    const tpdm_block_weights& b = ctx->blocks[i];
-    TPDM_CHECK(b.qkv_w && b.qkv_b && b.cqkv_w && b.cqkv_b && b.out_w && b.out_b && b.ff1_w && b.ff1_b && b.ff2_w && b.ff2_b, TPDM_ERR_ARG,
-               "tpdm_set_weights: block %d is missing weights", i);
-    if (ctx->cfg.qk_norm)
-      TPDM_CHECK(b.norm_q && b.norm_k && b.norm_added_q && b.norm_added_k, TPDM_ERR_ARG, "block %d: qk_norm weights missing", i);
+  ctx->has_mmdit = w->blocks != nullptr;
+  ctx->has_tpm = w->tpm_conv1_w != nullptr;
+  TPDM_CHECK(ctx->has_mmdit || ctx->has_tpm, TPDM_ERR_ARG, "tpdm_set_weights: neither MMDiT nor TimePredictor weights given");
+  if (ctx->has_mmdit) {
+    ctx->blocks.assign(w->blocks, w->blocks + ctx->cfg.num_layers);
+    ctx->w.blocks = ctx->blocks.data();
+    const void* req[] = {w->patch_w, w->patch_b, w->pos_table, w->t_w1, w->t_b1, w->t_w2, w->t_b2, w->p_w1, w->p_b1, w->p_w2, w->p_b2,
+                         w->ctx_w, w->ctx_b, w->adaln_w, w->adaln_b, w->proj_w, w->proj_b};
+    for (const void* p : req) TPDM_CHECK(p != nullptr, TPDM_ERR_ARG, "tpdm_set_weights: a required MMDiT weight pointer is null");
+    for (int i = 0; i < ctx->cfg.num_layers; ++i) {
+      const tpdm_block_weights& b = ctx->blocks[i];
+      TPDM_CHECK(b.qkv_w && b.qkv_b && b.cqkv_w && b.cqkv_b && b.out_w && b.out_b && b.ff1_w && b.ff1_b && b.ff2_w && b.ff2_b, TPDM_ERR_ARG,
+                 "tpdm_set_weights: block %d is missing weights", i);
+      if (ctx->cfg.qk_norm)
+        TPDM_CHECK(b.norm_q && b.norm_k && b.norm_added_q && b.norm_added_k, TPDM_ERR_ARG, "block %d: qk_norm weights missing", i);
+    }
+  }
+  if (ctx->has_tpm) {
+    const void* req[] = {w->tpm_conv1_b, w->tpm_lin_w, w->tpm_lin_b, w->tpm_gn_w, w->tpm_gn_b, w->tpm_conv2_w, w->tpm_conv2_b,
+                         w->tpm_fc1_w, w->tpm_fc1_b, w->tpm_fc2_w, w->tpm_fc2_b};
+    for (const void* p : req) TPDM_CHECK(p != nullptr, TPDM_ERR_ARG, "tpdm_set_weights: a required TimePredictor weight pointer is null");
   }
   ctx->has_weights = true;
   return 0;
@@ -365,6 +378,7 @@ int tpdm_plan_destroy(tpdm_plan* plan) {
 int tpdm_mmdit_forward(tpdm_plan* p, const float* latents, const float* timestep, const float* enc, const float* pooled, float* out_sample,
                        float* out_temb, float* out_h1, float* out_h2, void* stream) {
   TPDM_CHECK(p && latents && timestep && enc && pooled, TPDM_ERR_ARG, "tpdm_mmdit_forward: null argument");
+  TPDM_CHECK(p->ctx->has_mmdit, TPDM_ERR_STATE, "tpdm_mmdit_forward: MMDiT weights were not set");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const tpdm_ctx* ctx = p->ctx;
   TPDM_TRY(set_prompts(p, enc, nullptr, pooled, nullptr, s));
@@ -378,9 +392,10 @@ int tpdm_mmdit_forward(tpdm_plan* p, const float* latents, const float* timestep
 
 int tpdm_tpm_forward(tpdm_plan* p, const float* x_nchw, const float* temb, float* out_alpha_beta, void* stream) {
   TPDM_CHECK(p && x_nchw && temb && out_alpha_beta, TPDM_ERR_ARG, "tpdm_tpm_forward: null argument");
+  TPDM_CHECK(p->ctx->has_tpm, TPDM_ERR_STATE, "tpdm_tpm_forward: TimePredictor weights were not set");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  TPDM_TRY(k_nchw_to_nhwc_bf16(x_nchw, p->tpm_x, p->B, 2 * p->ctx->D, p->g, s));
-  return run_tpm(p, p->B, temb, out_alpha_beta, s);
+  TPDM_TRY(k_nchw_to_nhwc_bf16(x_nchw, p->tpm_x, p->Bt, 2 * p->ctx->D, p->g, s));
+  return run_tpm(p, p->Bt, temb, out_alpha_beta, s);
 }
 
 int tpdm_euler_step(const float* model_output, const float* sigma_next, const float* sigma, const float* sample, float* prev_sample,
@@ -391,16 +406,18 @@ int tpdm_euler_step(const float* model_output, const float* sigma_next, const fl
 }
 
 int tpdm_sample_begin(tpdm_plan* p, const float* latents, const float* neg_embeds, const float* pos_embeds, const float* neg_pooled,
-                      const float* pos_pooled, float guidance_scale, int predict, const float* ratios, void* stream) {
+                      const float* pos_pooled, float guidance_scale, int predict, const float* ratios, unsigned long long seed,
+                      void* stream) {
   TPDM_CHECK(p && latents && neg_embeds && pos_embeds && neg_pooled && pos_pooled, TPDM_ERR_ARG, "tpdm_sample_begin: null argument");
   TPDM_CHECK(p->cfg_pairs, TPDM_ERR_STATE, "tpdm_sample_begin: the plan was created without cfg_pairs");
-  TPDM_CHECK(predict || ratios, TPDM_ERR_ARG, "tpdm_sample_begin: predict == 0 needs injected ratios");
+  TPDM_CHECK(p->ctx->has_mmdit && p->ctx->has_tpm, TPDM_ERR_STATE, "tpdm_sample_begin: needs both MMDiT and TimePredictor weights");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const tpdm_ctx* ctx = p->ctx;
   const size_t lat = static_cast<size_t>(p->B) * ctx->cfg.in_channels * p->Hl * p->Wl;
   p->guidance = guidance_scale;
   p->predict = predict ? 1 : 0;
   p->have_ratios = ratios ? 1 : 0;
+  p->seed = seed;
   TPDM_CUDA_OK(cudaMemcpyAsync(p->latents, latents, lat * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if (ratios)
     TPDM_CUDA_OK(cudaMemcpyAsync(p->ratios, ratios, static_cast<size_t>(p->B) * p->max_steps * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -424,8 +441,12 @@ int tpdm_sample_step(tpdm_plan* p, int step, void* stream) {
   const tpdm_ctx* ctx = p->ctx;
   const int D = ctx->D, B = p->B, T1 = p->max_steps + 1;
   const size_t lat = static_cast<size_t>(B) * ctx->cfg.in_channels * p->Hl * p->Wl;
+  // a step enqueued after the batch finished (all_done[step-1] set, modeling_sd3_pnt.py:608) turns into empty launches
+  set_skip_flag(step > 0 ? p->all_done + (step - 1) : nullptr);
   // timestep = sigma.repeat(2) * 1000 (modeling_sd3_pnt.py:526); latents duplicated inside patchify (:524)
-  TPDM_TRY(run_mmdit(p, p->latents, B, 2, p->sigma_hist + step, T1, 1000.0f, 2, nullptr, nullptr, true, s));
+  int st_mm = run_mmdit(p, p->latents, B, 2, p->sigma_hist + step, T1, 1000.0f, 2, nullptr, nullptr, true, s);
+  set_skip_flag(nullptr);
+  TPDM_TRY(st_mm);
   TPDM_TRY(k_cfg_combine(p->temb, p->temb_cfg, p->tembs + static_cast<size_t>(step) * B * D, B, D, p->guidance, s));
   TPDM_TRY(run_tpm(p, B, p->temb_cfg, p->alpha_beta, s));
   ScheduleArgs a;
@@ -437,6 +458,7 @@ int tpdm_sample_step(tpdm_plan* p, int step, void* stream) {
   a.masks = p->masks;
   a.all_done = p->all_done;
   a.ratios = p->have_ratios ? p->ratios : nullptr;
+  a.seed = p->seed;
   a.B = B;
   a.T = p->max_steps;
   a.step = step;

@@ -44,6 +44,7 @@ struct AttnSmem {
 template <int DP>
 __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attention_tcgen05_kernel(const __grid_constant__ AttnOp A) {
   using L = AttnSmem<DP>;
+  if (A.skip != nullptr && *A.skip != 0) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -304,7 +305,11 @@ int attn_launch_impl(const AttnOp& op, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(op.q_tiles, op.H, op.Bt);
+  const double q_rows = op.q_tiles * kQT < op.S ? op.q_tiles * kQT : op.S;
+  prof_begin(1, 4.0 * op.Bt * op.H * q_rows * op.S * op.head_dim, stream);
   joint_attention_tcgen05_kernel<DP><<<grid, kAttnThreads, AttnSmem<DP>::kTotal, stream>>>(op);
+  prof_end(stream);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -320,6 +325,7 @@ int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int 
   op->H = H;
   op->Bt = Bt;
   op->dp = dp;
+  op->head_dim = head_dim;
   op->q_tiles = (S + kQT - 1) / kQT;
   op->scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   op->out = reinterpret_cast<__nv_bfloat16*>(out);
@@ -334,7 +340,10 @@ int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int 
   return 0;
 }
 
-int attn_launch(const AttnOp* op, cudaStream_t stream) {
+int attn_launch(const AttnOp* op_in, cudaStream_t stream) {
+  AttnOp op_copy = *op_in;
+  op_copy.skip = skip_flag();
+  const AttnOp* op = &op_copy;
   return op->dp == 64 ? attn_launch_impl<64>(*op, stream) : attn_launch_impl<128>(*op, stream);
 }
 

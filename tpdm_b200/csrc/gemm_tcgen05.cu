@@ -33,6 +33,7 @@ struct GemmParams {
   GemmOp op[2];
   int n_ops;
   int total_tiles;
+  const int* skip;
 };
 
 template <int BN>
@@ -65,6 +66,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams P) {
   using L = GemmSmem<BN>;
+  if (P.skip != nullptr && *P.skip != 0) return;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + L::kRing);
@@ -249,7 +251,12 @@ int launch_impl(const GemmParams& P, cudaStream_t stream) {
     attr_set = true;
   }
   int grid = P.total_tiles < num_sms() ? P.total_tiles : num_sms();
+  double flops = 0;
+  for (int i = 0; i < P.n_ops; ++i) flops += 2.0 * P.op[i].batch * P.op[i].rows_per_batch * static_cast<double>(P.op[i].N) * P.op[i].K;
+  prof_begin(0, flops, stream);
   gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(P);
+  prof_end(stream);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -318,6 +325,7 @@ int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {
   GemmParams P;
   P.n_ops = n_ops;
   P.total_tiles = 0;
+  P.skip = skip_flag();
   for (int i = 0; i < n_ops; ++i) {
     P.op[i] = ops[i];
     P.total_tiles += ops[i].num_tiles;

@@ -35,6 +35,16 @@ int fail(int code, const char* fmt, ...);
 
 int num_sms();
 
+// launch accounting + optional CUDA-event brackets per kernel class (bench.py roofline); class 0 = GEMM, 1 = attention
+void count_launch();
+void prof_begin(int cls, double flops, cudaStream_t s);
+void prof_end(cudaStream_t s);
+
+// Device flag checked at the top of the heavy kernels: when *flag != 0 the launch returns immediately.  Used so that a
+// denoising step enqueued speculatively after the trajectory has finished costs only empty launches.
+void set_skip_flag(const int* device_flag);
+const int* skip_flag();
+
 // bf16 tiled tensor map with 128-byte swizzle.  dims/strides innermost first; strides (bytes) for dims 1..rank-1.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box);
@@ -79,8 +89,9 @@ int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream);
 struct alignas(64) AttnOp {
   CUtensorMap tmQ, tmK, tmV;  // (dp, S, H, Bt) views of the token-major qkv buffer, box (64, 128, 1, 1)
   int S, H, Bt, dp;           // dp = padded head dim (64 or 128)
-  int q_tiles;
+  int q_tiles, head_dim;
   float scale_log2;           // log2(e) / sqrt(head_dim)
+  const int* skip;            // see set_skip_flag
   __nv_bfloat16* out;         // [Bt][S][H*dp]
 };
 int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int head_dim, void* out);

@@ -1,5 +1,6 @@
 // tpdm_b200 -- bandwidth-bound kernels of the TPDM step (sm_100a): vectorised, coalesced, warp-shuffle reduced.
 // Each kernel names the reference code it replaces (paths relative to /root/reference).
+#include <curand_kernel.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -133,6 +134,7 @@ int gemv_launch(const WT* W, const float* bias, const float* x, int ldx, const f
   }
   const int rows_per_block = kGemvWarps * kGemvRowsPerWarp;
   gemv_kernel<WT><<<(J + rows_per_block - 1) / rows_per_block, kGemvWarps * 32, smem, s>>>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -211,9 +213,11 @@ struct LnParams {
   LnSeg seg[2];
   int nseg, D;
   long long rows0, rows_total;
+  const int* skip;
 };
 
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnParams P) {
+  if (P.skip != nullptr && *P.skip != 0) return;
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= P.rows_total) return;
@@ -486,6 +490,25 @@ __global__ void tpm_tail_kernel(const float* __restrict__ y2, int go, int C, con
   }
 }
 
+// Gamma(shape, 1) by Marsaglia-Tsang (shape < 1 boosted through Gamma(shape + 1) * U^(1/shape))
+__device__ float gamma_draw(curandStatePhilox4_32_10_t* st, float shape) {
+  float boost = 1.f;
+  if (shape < 1.f) {
+    boost = powf(curand_uniform(st), 1.f / shape);
+    shape += 1.f;
+  }
+  const float d = shape - 1.f / 3.f, c = rsqrtf(9.f * d);
+  for (int it = 0; it < 64; ++it) {
+    const float x = curand_normal(st);
+    float v = 1.f + c * x;
+    if (v <= 0.f) continue;
+    v = v * v * v;
+    const float u = curand_uniform(st);
+    if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) return boost * d * v;
+  }
+  return boost * d;
+}
+
 // schedule update (modeling_sd3_pnt.py:557-590, 608)
 __global__ void schedule_kernel(const ScheduleArgs a) {
   const int i = threadIdx.x;
@@ -501,7 +524,17 @@ __global__ void schedule_kernel(const ScheduleArgs a) {
       beta = (1.f - p1) * (p2 - 2.f) + 1.f;
     }
     const float sigma = a.sigma_hist[i * (a.T + 1) + a.step];
-    float ratio = a.predict ? (alpha - 1.f) / (alpha + beta - 2.f) : a.ratios[i * a.T + a.step];
+    float ratio;
+    if (a.predict) {
+      ratio = (alpha - 1.f) / (alpha + beta - 2.f);  // Beta.mode (:567)
+    } else if (a.ratios) {
+      ratio = a.ratios[i * a.T + a.step];
+    } else {  // Beta.sample() (:569) = Ga / (Ga + Gb)
+      curandStatePhilox4_32_10_t st;
+      curand_init(a.seed, static_cast<unsigned long long>(i), static_cast<unsigned long long>(a.step) * 1024ull, &st);
+      const float ga = gamma_draw(&st, alpha), gb = gamma_draw(&st, beta);
+      ratio = ga / (ga + gb);
+    }
     float sigma_next;
     if (a.relative) {
       ratio = fminf(fmaxf(ratio, a.epsilon), 1.f - a.epsilon);
@@ -542,12 +575,14 @@ int k_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
   long long blocks = (n / 4 + 255) / 256;
   blocks = blocks < 1 ? 1 : (blocks > 148 * 16 ? 148 * 16 : blocks);
   cast_bf16_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(in, out, n);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int k_timestep_embedding(const float* timestep, int t_stride, float scale, float* out, int Bt, int rep, cudaStream_t s) {
   timestep_embedding_kernel<<<Bt, 128, 0, s>>>(timestep, t_stride, scale, out, Bt, rep);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -571,6 +606,7 @@ int k_patchify(const float* latents, const float* Wp, const float* bias, const f
   dim3 grid(N / kPatchTok, Bl);
   patchify_kernel<<<grid, 256, kPatchTok * 64 * sizeof(float), s>>>(latents, Wp, bias, pos_table, pos_max, x, Bl, dup, C, Hl, Wl, D,
                                                                    h1_out, tpm_x);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -580,11 +616,13 @@ int k_ln_modulate(const LnSeg* segs, int nseg, int D, cudaStream_t s) {
   LnParams P;
   P.nseg = nseg;
   P.D = D;
+  P.skip = skip_flag();
   P.seg[0] = segs[0];
   P.seg[1] = nseg > 1 ? segs[1] : segs[0];
   P.rows0 = static_cast<long long>(segs[0].rows) * segs[0].batch;
   P.rows_total = P.rows0 + (nseg > 1 ? static_cast<long long>(segs[1].rows) * segs[1].batch : 0);
   ln_modulate_kernel<<<blocks_for(P.rows_total, 8), 256, 0, s>>>(P);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -593,6 +631,7 @@ int k_norm_out(const float* x, bf16* xn, const float* shift, const float* scale,
                int g, float guidance, bf16* tpm_x, float* h2_out, cudaStream_t s) {
   norm_out_kernel<<<blocks_for(static_cast<long long>(B) * N, 8), 256, 0, s>>>(x, xn, shift, scale, mod_stride, B, cfg_pairs, N, D, g,
                                                                                guidance, tpm_x, h2_out);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -600,6 +639,7 @@ int k_norm_out(const float* x, bf16* xn, const float* shift, const float* scale,
 int k_qk_rmsnorm(bf16* qkv, int Bt, int S, int row0, int rows, int H, int dp, int d, const float* wq, const float* wk, cudaStream_t s) {
   const long long total = static_cast<long long>(Bt) * rows * 2 * H;
   qk_rmsnorm_kernel<<<blocks_for(total, 8), 256, 0, s>>>(qkv, Bt, S, row0, rows, H, dp, d, wq, wk);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -609,6 +649,7 @@ int k_unpatchify(const float* pout, int B, int cfg_pairs, float guidance, int C,
   const long long total = static_cast<long long>(B) * C * Hl * Wl;
   unpatchify_kernel<<<blocks_for(total, 256), 256, 0, s>>>(pout, B, cfg_pairs, guidance, C, Hl, Wl, velocity, latents, sigma, sigma_next,
                                                           sigma_stride, history);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -616,12 +657,14 @@ int k_unpatchify(const float* pout, int B, int cfg_pairs, float guidance, int C,
 int k_euler(const float* v, const float* sigma_next, const float* sigma, const float* sample, float* prev, int B, long long n,
             cudaStream_t s) {
   euler_kernel<<<blocks_for(static_cast<long long>(B) * n, 256), 256, 0, s>>>(v, sigma_next, sigma, sample, prev, B, n);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int k_cfg_combine(const float* in, float* out, float* out2, int B, int n, float guidance, cudaStream_t s) {
   cfg_combine_kernel<<<blocks_for(static_cast<long long>(B) * n, 256), 256, 0, s>>>(in, out, out2, B, n, guidance);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -629,6 +672,7 @@ int k_cfg_combine(const float* in, float* out, float* out2, int B, int n, float 
 int k_nchw_to_nhwc_bf16(const float* x, bf16* out, int B, int C, int g, cudaStream_t s) {
   dim3 grid((g * g + 31) / 32, (C + 31) / 32, B), block(32, 8);
   nchw_to_nhwc_bf16_kernel<<<grid, block, 0, s>>>(x, out, B, C, g);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -637,6 +681,7 @@ int k_gn_stats(const float* y, double* stats, int B, long long n, cudaStream_t s
   TPDM_CHECK(n % 4 == 0, TPDM_ERR_SHAPE, "gn_stats: n must be a multiple of 4");
   dim3 grid(64, B);
   gn_stats_kernel<<<grid, 256, 0, s>>>(y, stats, n);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -644,6 +689,7 @@ int k_gn_stats(const float* y, double* stats, int B, long long n, cudaStream_t s
 int k_gn_mod_silu(const float* y, const double* stats, const float* gn_w, const float* gn_b, const float* emb, float* a, int B, int npix,
                   int C, cudaStream_t s) {
   gn_mod_silu_kernel<<<blocks_for(static_cast<long long>(B) * npix * C, 256), 256, 0, s>>>(y, stats, gn_w, gn_b, emb, a, B, npix, C);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -654,6 +700,7 @@ int k_conv3x3_s2(const float* a, const float* w, const float* bias, float* y, in
   dim3 grid((go + kC2Pix - 1) / kC2Pix, go, B);
   const size_t smem = static_cast<size_t>(3) * (2 * kC2Pix + 1) * C * sizeof(float);
   conv3x3_s2_kernel<<<grid, C, smem, s>>>(a, w, bias, y, g, C);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -662,15 +709,16 @@ int k_tpm_tail(const float* y2, int B, int go, int C, const float* fc1_w, const 
                float eps, float* alpha_beta, cudaStream_t s) {
   TPDM_CHECK(C <= 128, TPDM_ERR_SHAPE, "tpm_tail: conv_out_channels %d > 128", C);
   tpm_tail_kernel<<<B, 128, 0, s>>>(y2, go, C, fc1_w, fc1_b, fc2_w, fc2_b, eps, alpha_beta);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int k_schedule(const ScheduleArgs& a, cudaStream_t s) {
   TPDM_CHECK(a.B <= 1024, TPDM_ERR_SHAPE, "schedule: batch %d > 1024", a.B);
-  TPDM_CHECK(a.predict || a.ratios, TPDM_ERR_ARG, "schedule: predict == 0 needs injected ratios");
   const int threads = ((a.B + 31) / 32) * 32;
   schedule_kernel<<<1, threads, 0, s>>>(a);
+  count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
 }

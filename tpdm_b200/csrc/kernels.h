@@ -70,7 +70,8 @@ struct ScheduleArgs {
   float *alphas, *betas, *logprobs;  // [B][T]
   int* masks;               // [B][T]
   int* all_done;            // [T]
-  const float* ratios;      // [B][T] or null
+  const float* ratios;      // [B][T] injected Beta draws, or null: draw on the device (Philox, Marsaglia-Tsang)
+  unsigned long long seed;
   int B, T, step, predict, relative, prediction_type;
   float min_sigma, epsilon;
 };

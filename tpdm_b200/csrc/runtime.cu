@@ -1,7 +1,9 @@
 // tpdm_b200 -- error reporting, device queries and TMA descriptor encoding shared by the library.
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "host.h"
 
@@ -19,6 +21,36 @@ int fail(int code, const char* fmt, ...) {
   va_end(ap);
   g_last_error = buf;
   return code;
+}
+
+static thread_local const int* g_skip = nullptr;
+void set_skip_flag(const int* f) { g_skip = f; }
+const int* skip_flag() { return g_skip; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct Profiler {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cls;
+  std::vector<double> flops;
+  size_t n = 0;
+  bool on = false;
+};
+Profiler g_prof;
+}  // namespace
+
+void prof_begin(int cls, double flops, cudaStream_t s) {
+  if (!g_prof.on || 2 * (g_prof.n + 1) > g_prof.ev.size()) return;
+  g_prof.cls[g_prof.n] = cls;
+  g_prof.flops[g_prof.n] = flops;
+  cudaEventRecord(g_prof.ev[2 * g_prof.n], s);
+}
+void prof_end(cudaStream_t s) {
+  if (!g_prof.on || 2 * (g_prof.n + 1) > g_prof.ev.size()) return;
+  cudaEventRecord(g_prof.ev[2 * g_prof.n + 1], s);
+  ++g_prof.n;
 }
 
 int num_sms() {
@@ -79,3 +111,43 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 extern "C" const char* tpdm_last_error(void) { return tpdm::g_last_error.c_str(); }
 extern "C" int tpdm_abi_version(void) { return TPDM_ABI_VERSION; }
+
+extern "C" long long tpdm_launch_count(int reset) {
+  long long v = tpdm::g_launches.load();
+  if (reset) tpdm::g_launches.store(0);
+  return v;
+}
+
+extern "C" int tpdm_profile_start(int max_records) {
+  using namespace tpdm;
+  TPDM_CHECK(max_records > 0, TPDM_ERR_ARG, "tpdm_profile_start: max_records must be positive");
+  while (g_prof.ev.size() < static_cast<size_t>(2 * max_records)) {
+    cudaEvent_t e;
+    TPDM_CUDA_OK(cudaEventCreate(&e));
+    g_prof.ev.push_back(e);
+  }
+  g_prof.cls.assign(max_records, 0);
+  g_prof.flops.assign(max_records, 0.0);
+  g_prof.n = 0;
+  g_prof.on = true;
+  return 0;
+}
+
+extern "C" int tpdm_profile_stop(double* ms, double* flops, long long* count, int n_classes) {
+  using namespace tpdm;
+  TPDM_CHECK(ms && flops && count && n_classes > 0, TPDM_ERR_ARG, "tpdm_profile_stop: null argument");
+  g_prof.on = false;
+  for (int c = 0; c < n_classes; ++c) ms[c] = flops[c] = 0.0, count[c] = 0;
+  if (g_prof.n > 0) TPDM_CUDA_OK(cudaEventSynchronize(g_prof.ev[2 * g_prof.n - 1]));
+  for (size_t i = 0; i < g_prof.n; ++i) {
+    float t = 0.f;
+    TPDM_CUDA_OK(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    const int c = g_prof.cls[i];
+    if (c >= 0 && c < n_classes) {
+      ms[c] += t;
+      flops[c] += g_prof.flops[i];
+      count[c] += 1;
+    }
+  }
+  return 0;
+}

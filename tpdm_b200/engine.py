@@ -1,0 +1,346 @@
+"""Host-side engine: packs module weights for libtpdm_b200.so, owns shape-bound plans (workspace + prebuilt TMA
+descriptors) and drives the adaptive loop.  PyTorch is used for device memory and streams only; every arithmetic
+operation of the path runs inside the C-ABI library (no eager fallback exists).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(dtype=torch.float32).contiguous()
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(dtype=torch.bfloat16).contiguous()
+
+
+def _pad_heads_rows(w: torch.Tensor, heads: int, d: int, dp: int) -> torch.Tensor:
+    """[heads*d, ...] -> [heads*dp, ...] with zero rows for the padded head dims."""
+    if d == dp:
+        return w
+    rest = w.shape[1:]
+    out = w.new_zeros((heads, dp) + tuple(rest))
+    out[:, :d] = w.reshape((heads, d) + tuple(rest))
+    return out.reshape((heads * dp,) + tuple(rest))
+
+
+class PackedWeights:
+    """Device tensors in the layout include/tpdm_b200.h documents, plus the ctypes structs pointing at them."""
+
+    def __init__(self):
+        self.keep = []           # owning references
+        self.struct = L.TpdmWeights()
+        self.blocks = None
+
+    def _set(self, struct, name, tensor):
+        self.keep.append(tensor)
+        setattr(struct, name, tensor.data_ptr())
+
+
+def pack_transformer(pw: PackedWeights, sd: Dict[str, torch.Tensor], cfg, device) -> None:
+    """diffusers-layout state dict of CustomSD3Transformer2DModel -> tpdm_weights (MMDiT part)."""
+    H, d = cfg.num_attention_heads, cfg.attention_head_dim
+    D = H * d
+    dp = 64 if d <= 64 else 128
+    Lyr = cfg.num_layers
+    g = lambda k: sd[k].to(device)
+    s = pw.struct
+    pw._set(s, "patch_w", _f32(g("pos_embed.proj.weight").reshape(D, -1)))
+    pw._set(s, "patch_b", _f32(g("pos_embed.proj.bias")))
+    pw._set(s, "pos_table", _f32(g("pos_embed.pos_embed").reshape(-1, D)))
+    for short, base in (("t", "time_text_embed.timestep_embedder"), ("p", "time_text_embed.text_embedder")):
+        pw._set(s, f"{short}_w1", _f32(g(base + ".linear_1.weight")))
+        pw._set(s, f"{short}_b1", _f32(g(base + ".linear_1.bias")))
+        pw._set(s, f"{short}_w2", _f32(g(base + ".linear_2.weight")))
+        pw._set(s, f"{short}_b2", _f32(g(base + ".linear_2.bias")))
+    pw._set(s, "ctx_w", _bf16(g("context_embedder.weight")))
+    pw._set(s, "ctx_b", _f32(g("context_embedder.bias")))
+    pw._set(s, "proj_w", _bf16(g("proj_out.weight")))
+    pw._set(s, "proj_b", _f32(g("proj_out.bias")))
+    ada_w, ada_b = [], []
+    blocks = (L.TpdmBlockWeights * Lyr)()
+    for i in range(Lyr):
+        p = f"transformer_blocks.{i}."
+        last = i == Lyr - 1
+        ada_w += [g(p + "norm1.linear.weight"), g(p + "norm1_context.linear.weight")]
+        ada_b += [g(p + "norm1.linear.bias"), g(p + "norm1_context.linear.bias")]
+        b = blocks[i]
+
+        def fused(names):
+            w = torch.cat([_pad_heads_rows(g(p + f"attn.{n}.weight"), H, d, dp) for n in names], 0)
+            bias = torch.cat([_pad_heads_rows(g(p + f"attn.{n}.bias"), H, d, dp) for n in names], 0)
+            return _bf16(w), _f32(bias)
+
+        def out_proj(name):
+            w = g(p + f"attn.{name}.weight")  # [D, H*d] -> [D, H*dp]
+            if d != dp:
+                w = _pad_heads_rows(w.t().contiguous(), H, d, dp).t().contiguous()
+            return _bf16(w), _f32(g(p + f"attn.{name}.bias"))
+
+        for field, (w, bias) in (("qkv", fused(("to_q", "to_k", "to_v"))), ("cqkv", fused(("add_q_proj", "add_k_proj", "add_v_proj"))),
+                                 ("out", out_proj("to_out.0"))):
+            pw._set(b, field + "_w", w)
+            pw._set(b, field + "_b", bias)
+        pw._set(b, "ff1_w", _bf16(g(p + "ff.net.0.proj.weight")))
+        pw._set(b, "ff1_b", _f32(g(p + "ff.net.0.proj.bias")))
+        pw._set(b, "ff2_w", _bf16(g(p + "ff.net.2.weight")))
+        pw._set(b, "ff2_b", _f32(g(p + "ff.net.2.bias")))
+        if not last:
+            w, bias = out_proj("to_add_out")
+            pw._set(b, "cout_w", w)
+            pw._set(b, "cout_b", bias)
+            pw._set(b, "cff1_w", _bf16(g(p + "ff_context.net.0.proj.weight")))
+            pw._set(b, "cff1_b", _f32(g(p + "ff_context.net.0.proj.bias")))
+            pw._set(b, "cff2_w", _bf16(g(p + "ff_context.net.2.weight")))
+            pw._set(b, "cff2_b", _f32(g(p + "ff_context.net.2.bias")))
+        if cfg.qk_norm == "rms_norm":
+            for field, name in (("norm_q", "norm_q"), ("norm_k", "norm_k"), ("norm_added_q", "norm_added_q"),
+                                ("norm_added_k", "norm_added_k")):
+                w = g(p + f"attn.{name}.weight")
+                wp = w.new_zeros(dp)
+                wp[:d] = w
+                pw._set(b, field, _f32(wp))
+    ada_w.append(g("norm_out.linear.weight"))
+    ada_b.append(g("norm_out.linear.bias"))
+    pw._set(s, "adaln_w", _bf16(torch.cat(ada_w, 0)))
+    pw._set(s, "adaln_b", _f32(torch.cat(ada_b, 0)))
+    assert pw.keep[-1].numel() == 12 * D * Lyr - 2 * D
+    pw.blocks = blocks
+    s.blocks = C.cast(blocks, C.POINTER(L.TpdmBlockWeights))
+
+
+def pack_time_predictor(pw: PackedWeights, sd: Dict[str, torch.Tensor], device) -> None:
+    """TimePredictor state dict (modeling_sd3_pnt.py:85-126 names) -> tpdm_weights (TPM part)."""
+    g = lambda k: sd[k].to(device)
+    s = pw.struct
+    c1 = g("conv1.weight")  # [C1, 2D, 3, 3] -> [C1, 9, 2D]
+    pw._set(s, "tpm_conv1_w", _bf16(c1.permute(0, 2, 3, 1).reshape(c1.shape[0], -1)))
+    pw._set(s, "tpm_conv1_b", _f32(g("conv1.bias")))
+    pw._set(s, "tpm_lin_w", _f32(g("norm1.linear.weight")))
+    pw._set(s, "tpm_lin_b", _f32(g("norm1.linear.bias")))
+    pw._set(s, "tpm_gn_w", _f32(g("norm1.norm.weight")))
+    pw._set(s, "tpm_gn_b", _f32(g("norm1.norm.bias")))
+    c2 = g("conv2.weight")  # [oc, c, 3, 3] -> [9, c, oc]
+    pw._set(s, "tpm_conv2_w", _f32(c2.permute(2, 3, 1, 0).reshape(9, c2.shape[1], c2.shape[0])))
+    pw._set(s, "tpm_conv2_b", _f32(g("conv2.bias")))
+    pw._set(s, "tpm_fc1_w", _f32(g("fc1.weight")))
+    pw._set(s, "tpm_fc1_b", _f32(g("fc1.bias")))
+    pw._set(s, "tpm_fc2_w", _f32(g("fc2.weight")))
+    pw._set(s, "tpm_fc2_b", _f32(g("fc2.bias")))
+
+
+class Plan:
+    """A shape-bound workspace with typed torch views over the library's state buffers."""
+
+    def __init__(self, engine: "Engine", batch: int, cfg_pairs: bool, latent: int, n_text: int, max_steps: int):
+        lib = L.load()
+        self.engine, self.batch, self.cfg_pairs, self.latent, self.n_text, self.max_steps = engine, batch, cfg_pairs, latent, n_text, max_steps
+        nbytes = lib.tpdm_plan_workspace_bytes(engine.ctx, batch, int(cfg_pairs), latent, latent, n_text, max_steps)
+        if nbytes == 0:
+            L.check(L.TPDM_ERR_SHAPE if lib.tpdm_last_error() else L.TPDM_ERR_ARG)
+        self.workspace = torch.empty(nbytes + 1024, dtype=torch.uint8, device=engine.device)
+        base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        self._base_off = base - self.workspace.data_ptr()
+        handle = L.vp()
+        L.check(lib.tpdm_plan_create(engine.ctx, batch, int(cfg_pairs), latent, latent, n_text, max_steps, base, nbytes, C.byref(handle)))
+        self.handle = handle
+        self.state = None
+        if engine.has_mmdit and engine.has_tpm and cfg_pairs:
+            st = L.TpdmSampleState()
+            L.check(lib.tpdm_sample_state_get(handle, C.byref(st)))
+            cfg, D, g = engine.cfg, engine.D, latent // 2
+            Cc = cfg["in_channels"]
+            f32, i32 = torch.float32, torch.int32
+            self.state = dict(
+                latents=self._view(st.latents, f32, (batch, Cc, latent, latent)),
+                velocity=self._view(st.velocity, f32, (batch, Cc, latent, latent)),
+                sigma_hist=self._view(st.sigma_hist, f32, (batch, max_steps + 1)),
+                alphas=self._view(st.alphas, f32, (batch, max_steps)),
+                betas=self._view(st.betas, f32, (batch, max_steps)),
+                logprobs=self._view(st.logprobs, f32, (batch, max_steps)),
+                prob_masks=self._view(st.prob_masks, i32, (batch, max_steps)),
+                all_done=self._view(st.all_done, i32, (max_steps,)),
+                tembs=self._view(st.tembs, f32, (max_steps, batch, D)),
+                tpm_input=self._view(st.tpm_input, torch.bfloat16, (batch, g, g, 2 * D)),
+                history_latents=self._view(st.history_latents, f32, (max_steps, batch, Cc, latent, latent)),
+            )
+
+    def _view(self, ptr: int, dtype: torch.dtype, shape) -> torch.Tensor:
+        off = ptr - self.workspace.data_ptr()
+        n = 1
+        for s in shape:
+            n *= s
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        return self.workspace[off: off + nb].view(dtype).view(shape)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                L.load().tpdm_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class Engine:
+    """One per (transformer, time_predictor) pair and device."""
+
+    def __init__(self, cfg: dict, device: torch.device, transformer_sd: Optional[Dict[str, torch.Tensor]] = None, transformer_cfg=None,
+                 tpm_sd: Optional[Dict[str, torch.Tensor]] = None, min_sigma: float = 0.001, relative: bool = True,
+                 prediction_type: str = "alpha_beta", epsilon: float = 1e-3, tpm_epsilon: float = 1.0, tpm_channels: int = 128):
+        lib = L.load()
+        if device.type != "cuda":
+            raise RuntimeError("tpdm_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        if prediction_type not in ("alpha_beta", "mode_concentration"):
+            raise ValueError(f"unknown prediction_type {prediction_type!r}")
+        self.cfg, self.device = dict(cfg), device
+        self.D = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+        c = L.TpdmConfig(
+            num_layers=cfg["num_layers"], num_heads=cfg["num_attention_heads"], head_dim=cfg["attention_head_dim"],
+            joint_attention_dim=cfg["joint_attention_dim"], pooled_projection_dim=cfg["pooled_projection_dim"],
+            in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], patch_size=cfg["patch_size"],
+            pos_embed_max_size=cfg["pos_embed_max_size"], qk_norm=1 if cfg.get("qk_norm") == "rms_norm" else 0,
+            tpm_channels=tpm_channels, prediction_type=0 if prediction_type == "alpha_beta" else 1, relative=1 if relative else 0,
+            min_sigma=min_sigma, epsilon=epsilon, tpm_epsilon=tpm_epsilon)
+        with torch.cuda.device(device):
+            handle = L.vp()
+            L.check(lib.tpdm_create(C.byref(c), C.byref(handle)))
+            self.ctx = handle
+            self.weights = PackedWeights()
+            self.has_mmdit = transformer_sd is not None
+            self.has_tpm = tpm_sd is not None
+            if self.has_mmdit:
+                pack_transformer(self.weights, transformer_sd, transformer_cfg, device)
+            if self.has_tpm:
+                pack_time_predictor(self.weights, tpm_sd, device)
+            L.check(lib.tpdm_set_weights(self.ctx, C.byref(self.weights.struct)))
+        self.plans: Dict[Tuple, Plan] = {}
+        self.min_sigma = min_sigma
+
+    def __del__(self):
+        try:
+            self.plans.clear()
+            if getattr(self, "ctx", None):
+                L.load().tpdm_destroy(self.ctx)
+        except Exception:
+            pass
+
+    def plan(self, batch: int, cfg_pairs: bool, latent: int, n_text: int, max_steps: int = 1) -> Plan:
+        key = (batch, bool(cfg_pairs), latent, n_text, max_steps)
+        p = self.plans.get(key)
+        if p is None:
+            if len(self.plans) >= 4:  # bound the HBM held by cached workspaces
+                self.plans.pop(next(iter(self.plans)))
+            with torch.cuda.device(self.device):
+                p = Plan(self, batch, cfg_pairs, latent, n_text, max_steps)
+            self.plans[key] = p
+        return p
+
+    # ---- CustomSD3Transformer2DModel.forward -------------------------------------------------------------------
+    def mmdit_forward(self, hidden_states, encoder_hidden_states, pooled_projections, timestep):
+        lib = L.load()
+        Bt, Cc, h, w = hidden_states.shape
+        if h != w:
+            raise ValueError(f"only square latents are supported (got {h}x{w})")
+        n_text = encoder_hidden_states.shape[1]
+        plan = self.plan(Bt, False, h, n_text, 1)
+        dev, f32 = self.device, torch.float32
+        lat = hidden_states.to(device=dev, dtype=f32).contiguous()
+        enc = encoder_hidden_states.to(device=dev, dtype=f32).contiguous()
+        pooled = pooled_projections.to(device=dev, dtype=f32).contiguous()
+        ts = timestep.to(device=dev, dtype=f32).reshape(-1)
+        if ts.numel() == 1:
+            ts = ts.expand(Bt)
+        ts = ts.contiguous()
+        if enc.shape[0] != Bt or pooled.shape[0] != Bt or ts.shape[0] != Bt:
+            raise ValueError("batch sizes of hidden_states / encoder_hidden_states / pooled_projections / timestep differ")
+        N = (h // 2) * (w // 2)
+        out = torch.empty(Bt, self.cfg["out_channels"], h, w, device=dev, dtype=f32)
+        temb = torch.empty(Bt, self.D, device=dev, dtype=f32)
+        h1 = torch.empty(Bt, N, self.D, device=dev, dtype=f32)
+        h2 = torch.empty(Bt, N, self.D, device=dev, dtype=f32)
+        with torch.cuda.device(dev):
+            L.check(lib.tpdm_mmdit_forward(plan.handle, L.ptr(lat), L.ptr(ts), L.ptr(enc), L.ptr(pooled), L.ptr(out), L.ptr(temb),
+                                           L.ptr(h1), L.ptr(h2), L.stream_ptr()))
+        return out, temb, h1, h2
+
+    # ---- TimePredictor.forward ---------------------------------------------------------------------------------
+    def tpm_forward(self, x, temb):
+        lib = L.load()
+        B, C2, g, g2 = x.shape
+        if g != g2 or C2 != 2 * self.D:
+            raise ValueError(f"TimePredictor input must be (B, {2 * self.D}, g, g); got {tuple(x.shape)}")
+        plan = self.plan(B, False, 2 * g, 8, 1)
+        dev, f32 = self.device, torch.float32
+        xx = x.to(device=dev, dtype=f32).contiguous()
+        tt = temb.to(device=dev, dtype=f32).contiguous()
+        out = torch.empty(B, 2, device=dev, dtype=f32)
+        with torch.cuda.device(dev):
+            L.check(lib.tpdm_tpm_forward(plan.handle, L.ptr(xx), L.ptr(tt), L.ptr(out), L.stream_ptr()))
+        return out
+
+    # ---- the adaptive loop -------------------------------------------------------------------------------------
+    def sample(self, latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
+               max_inference_steps: int, guidance_scale: float, predict: bool, ratios=None, seed: int = 0,
+               record_tpm_inputs: bool = False, record_velocity: bool = False):
+        """Runs tpdm_sample_step until every sigma_next < min_sigma (checked one step late through a pinned flag, the
+        speculative extra step is skipped on the device) or max_inference_steps.  Returns a dict of device tensors."""
+        lib = L.load()
+        B, Cc, h, w = latents.shape
+        dev, f32 = self.device, torch.float32
+        plan = self.plan(B, True, h, prompt_embeds.shape[1], max_inference_steps)
+        st = plan.state
+        cvt = lambda t: t.to(device=dev, dtype=f32).contiguous()
+        lat, pe, ne, pp, npp = cvt(latents), cvt(prompt_embeds), cvt(negative_prompt_embeds), cvt(pooled_prompt_embeds), cvt(negative_pooled_prompt_embeds)
+        rt = None
+        if not predict and ratios is not None:
+            rt = cvt(ratios)
+            if rt.shape != (B, max_inference_steps):
+                raise ValueError(f"ratios must have shape {(B, max_inference_steps)}")
+        rec = vel = None
+        g = h // 2
+        if record_tpm_inputs:
+            rec = torch.empty(B, max_inference_steps, g, g, 2 * self.D, device=dev, dtype=torch.bfloat16)
+        if record_velocity:
+            vel = torch.empty(B, max_inference_steps, Cc, h, w, device=dev, dtype=f32)
+        done_host = torch.zeros(max_inference_steps, dtype=torch.int32).pin_memory()
+        events = []
+        executed = max_inference_steps
+        with torch.cuda.device(dev):
+            stream = L.stream_ptr()
+            L.check(lib.tpdm_sample_begin(plan.handle, L.ptr(lat), L.ptr(ne), L.ptr(pe), L.ptr(npp), L.ptr(pp), float(guidance_scale),
+                                          1 if predict else 0, L.ptr(rt) if rt is not None else None, int(seed) & (2**64 - 1), stream))
+            for step in range(max_inference_steps):
+                L.check(lib.tpdm_sample_step(plan.handle, step, stream))
+                if rec is not None:
+                    rec[:, step].copy_(st["tpm_input"])
+                if vel is not None:
+                    vel[:, step].copy_(st["velocity"])
+                done_host[step: step + 1].copy_(st["all_done"][step: step + 1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                events.append(ev)
+                if step >= 1:
+                    events[step - 1].synchronize()
+                    if int(done_host[step - 1]) != 0:
+                        executed = step  # steps [0, step) are real; step `step` was skipped on the device
+                        break
+            else:
+                events[-1].synchronize()
+        T = executed
+        out = dict(
+            steps=T,
+            sigmas=st["sigma_hist"][:, 1: T + 1].clone(), alphas=st["alphas"][:, :T].clone(), betas=st["betas"][:, :T].clone(),
+            logprobs_raw=st["logprobs"][:, :T].clone(), prob_masks=st["prob_masks"][:, :T].clone().bool(),
+            tembs=st["tembs"][:T].permute(1, 0, 2).clone(), history_latents=st["history_latents"][:T].permute(1, 0, 2, 3, 4).clone(),
+        )
+        if rec is not None:
+            out["tpm_inputs_nhwc"] = rec[:, :T]
+        if vel is not None:
+            out["velocities"] = vel[:, :T]
+        return out

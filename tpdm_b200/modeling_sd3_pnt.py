@@ -1,0 +1,420 @@
+"""Drop-in for /root/reference/src/models/stable_diffusion_3/modeling_sd3_pnt.py (the TPDM-wrapped SD3 pipeline).
+
+Same class names, constructor kwargs, method names and output fields as the reference; the denoising loop
+(modeling_sd3_pnt.py:522-612), the TimePredictor (:85-126) and the Euler update run in libtpdm_b200.so.
+Out of scope: the three text encoders and the VAE -- pass ``prompt_embeds`` etc.; ``images`` is
+filled only when a ``vae`` module with ``decode`` has been attached by the caller.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+from typing import List, Optional, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .engine import Engine
+from .model_utilis import CustomDiffusionModelOutput, CustomFlowMatchEulerDiscreteScheduler
+from .reference_distributions import get_ref_beta
+from .transformer_sd3 import CustomSD3Transformer2DModel
+
+logger = logging.getLogger(__name__)
+
+SD3_MEDIUM_TRANSFORMER_CONFIG = dict(
+    sample_size=128, patch_size=2, in_channels=16, num_layers=24, attention_head_dim=64, num_attention_heads=24,
+    joint_attention_dim=4096, caption_projection_dim=1536, pooled_projection_dim=2048, out_channels=16, pos_embed_max_size=192)
+
+
+def reshape_hidden_states_to_2d(hidden_states: torch.Tensor, height: int = 64, width: int = 64, patch_size: int = 2) -> torch.Tensor:
+    """modeling_sd3_pnt.py:33-54 (a pure re-indexing; the CUDA path folds it into its store addresses instead)."""
+    hidden_states = hidden_states.reshape(
+        shape=(hidden_states.shape[0], height // patch_size, width // patch_size, patch_size, patch_size, hidden_states.shape[-1]))
+    hidden_states = torch.einsum("nhwpqc->nchpwq", hidden_states)
+    return hidden_states.reshape(shape=(hidden_states.shape[0], hidden_states.shape[1], height, width))
+
+
+class CustomAdaGroupNormZeroSingle(nn.Module):
+    """Parameter container with the reference's names (modeling_sd3_pnt.py:56-83): ``linear`` (D -> 2C), ``norm`` = GroupNorm(1, C)."""
+
+    def __init__(self, input_dim: int, embedding_dim: int, norm_type="group_norm", bias=True, device=None, dtype=None):
+        super().__init__()
+        self.silu = nn.SiLU()
+        self.linear = nn.Linear(input_dim, 2 * embedding_dim, bias=bias, device=device, dtype=dtype)
+        if norm_type == "group_norm":
+            self.norm = nn.GroupNorm(1, embedding_dim, eps=1e-6, device=device, dtype=dtype)
+        else:
+            raise ValueError(f"Unsupported `norm_type` ({norm_type}) provided. Supported ones are: 'layer_norm', 'fp32_layer_norm'.")
+
+
+class TimePredictor(nn.Module):
+    """modeling_sd3_pnt.py:85-126.  forward(x (B, in_channels, g, g), temb (B, in_channels/2)) -> (B, 2) = (alpha, beta) > 1."""
+
+    def __init__(self, conv_out_channels, in_channels=1536 * 2, projection_dim=2, init_alpha=1.5, init_beta=0.5, device=None, dtype=None):
+        super().__init__()
+        if projection_dim != 2:
+            raise ValueError("projection_dim must be 2 (alpha, beta)")
+        fk = {"device": device, "dtype": dtype}
+        self.conv1 = nn.Conv2d(in_channels, conv_out_channels, kernel_size=(3, 3), padding=1, **fk)
+        self.conv2 = nn.Conv2d(conv_out_channels, conv_out_channels, kernel_size=(3, 3), padding=1, stride=2, **fk)
+        self.fc1 = nn.Linear(conv_out_channels, 128, **fk)
+        self.fc2 = nn.Linear(128, projection_dim, **fk)
+        self.norm1 = CustomAdaGroupNormZeroSingle(in_channels // 2, conv_out_channels, **fk)
+        self.epsilon = 1.0
+        self.init_alpha = init_alpha
+        self.init_beta = init_beta
+        self.in_channels, self.conv_out_channels = in_channels, conv_out_channels
+        self._init_weights()
+        self._engine: Optional[Engine] = None
+        self._engine_key = None
+
+    def _init_weights(self):
+        for m in self.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.normal_(m.weight, std=0.02)
+                if m.bias is not None and isinstance(m, nn.Conv2d):
+                    nn.init.constant_(m.bias, 0)
+        nn.init.constant_(self.fc1.bias, 0)
+        nn.init.constant_(self.fc2.bias[0], self.init_alpha)
+        nn.init.constant_(self.fc2.bias[1], self.init_beta)
+
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version, p.device) for p in self.parameters())
+
+    def _standalone_engine(self) -> Engine:
+        key = self._weights_key()
+        if self._engine is None or key != self._engine_key:
+            D = self.in_channels // 2
+            if D % 64 != 0:
+                raise ValueError("TimePredictor in_channels/2 must be a multiple of 64 for the CUDA path")
+            cfg = dict(num_layers=1, num_attention_heads=D // 64, attention_head_dim=64, joint_attention_dim=4096,
+                       pooled_projection_dim=2048, in_channels=16, out_channels=16, patch_size=2, pos_embed_max_size=192, qk_norm=None)
+            self._engine = Engine(cfg, self.fc2.weight.device, tpm_sd=self.state_dict(), tpm_epsilon=self.epsilon,
+                                  tpm_channels=self.conv_out_channels)
+            self._engine_key = key
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, x, temb):
+        return self._standalone_engine().tpm_forward(x, temb).to(x.dtype)
+
+
+class SD3PredictNextTimeStepModel(nn.Module):
+    def __init__(
+        self,
+        pretrained_model_name_or_path=None,
+        torch_dtype=torch.float16,
+        min_sigma=0.001,
+        init_alpha=1.5,
+        init_beta=0.5,
+        pre_process=False,
+        relative=True,
+        prediction_type="alpha_beta",
+        transformer_config: Optional[dict] = None,
+        device=None,
+    ):
+        """Reference kwargs (modeling_sd3_pnt.py:130-140) plus ``transformer_config`` / ``device`` for offline random-init
+        construction (the reference only has ``from_pretrained``)."""
+        super().__init__()
+        cfg = transformer_config
+        weights_file = None
+        if cfg is None:
+            if pretrained_model_name_or_path is None:
+                raise ValueError("give either pretrained_model_name_or_path or transformer_config")
+            cfg_path = os.path.join(pretrained_model_name_or_path, "transformer", "config.json")
+            if not os.path.isfile(cfg_path):
+                raise ValueError(f"{cfg_path} not found (no network: only local diffusers-layout checkpoints can be loaded)")
+            raw = json.load(open(cfg_path))
+            cfg = {k: raw[k] for k in SD3_MEDIUM_TRANSFORMER_CONFIG if k in raw}
+            for k in ("qk_norm", "dual_attention_layers"):
+                if k in raw:
+                    cfg[k] = raw[k]
+            weights_file = os.path.join(pretrained_model_name_or_path, "transformer", "diffusion_pytorch_model.safetensors")
+        self.vae = None            # out of scope; attach a module with .decode/.config to get images
+        self.transformer = CustomSD3Transformer2DModel(**cfg, device=device, dtype=torch_dtype)
+        if weights_file is not None and os.path.isfile(weights_file):
+            from safetensors.torch import load_file
+
+            self.transformer.load_state_dict(load_file(weights_file), strict=False)
+        self.time_predictor = TimePredictor(
+            conv_out_channels=128, in_channels=self.transformer.config.caption_projection_dim * 2, projection_dim=2,
+            init_alpha=init_alpha, init_beta=init_beta, device=device, dtype=torch_dtype)
+        self.scheduler = CustomFlowMatchEulerDiscreteScheduler()
+        self.pre_process = pre_process
+        self.vae_scale_factor = 8
+        self.tokenizer_max_length = 77
+        self.default_sample_size = self.transformer.config.sample_size
+        self.patch_size = self.transformer.config.patch_size
+        self.min_sigma = min_sigma
+        self.relative = relative
+        self.epsilon = 1e-3
+        self.prediction_type = prediction_type
+        self._engine: Optional[Engine] = None
+        self._engine_key = None
+        self.requires_grad_(False)
+        self.eval()
+
+    # ---------------------------------------------------------------------------------------------------------------
+    @property
+    def device(self):
+        return self.transformer.device
+
+    @property
+    def dtype(self):
+        return self.transformer.dtype
+
+    def get_engine(self) -> Engine:
+        key = (self.transformer._weights_key(), self.time_predictor._weights_key(), self.min_sigma, self.relative, self.prediction_type)
+        if self._engine is None or key != self._engine_key:
+            self._engine = Engine(self.transformer.engine_config(), self.device, transformer_sd=self.transformer.state_dict(),
+                                  transformer_cfg=self.transformer.config, tpm_sd=self.time_predictor.state_dict(),
+                                  min_sigma=self.min_sigma, relative=self.relative, prediction_type=self.prediction_type,
+                                  epsilon=self.epsilon, tpm_epsilon=self.time_predictor.epsilon,
+                                  tpm_channels=self.time_predictor.conv_out_channels)
+            self._engine_key = key
+        return self._engine
+
+    def encode_prompt(self, *args, **kwargs):
+        raise NotImplementedError(
+            "text encoders (CLIP-L, CLIP-G, T5-XXL) are outside the tpdm_b200 hot path: pass prompt_embeds, "
+            "negative_prompt_embeds, pooled_prompt_embeds and negative_pooled_prompt_embeds (SURVEY.md section 8f)")
+
+    def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
+        if latents is not None:
+            return latents.to(device=device, dtype=dtype)
+        shape = (batch_size, num_channels_latents, int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor)
+        return torch.randn(shape, generator=generator, device=device, dtype=dtype)
+
+    @torch.no_grad()
+    def forward(
+        self,
+        prompt: Union[str, List[str]] = None,
+        negative_prompt: Union[str, List[str]] = None,
+        prompt_embeds: Optional[torch.FloatTensor] = None,
+        negative_prompt_embeds: Optional[torch.FloatTensor] = None,
+        pooled_prompt_embeds: Optional[torch.FloatTensor] = None,
+        negative_pooled_prompt_embeds: Optional[torch.FloatTensor] = None,
+        num_images_per_prompt: int = 1,
+        max_inference_steps: int = 28,
+        guidance_scale: Union[float, None] = 7.0,
+        generator: Union[torch.Generator, List[torch.Generator]] = None,
+        latents: Optional[torch.FloatTensor] = None,
+        fix_sigmas: Optional[torch.FloatTensor] = None,
+        return_full_process_images: bool = False,
+        predict: bool = False,
+        ratios: Optional[torch.Tensor] = None,
+        return_velocities: bool = False,
+    ) -> CustomDiffusionModelOutput:
+        """Reference signature (modeling_sd3_pnt.py:447-463) + two additions:
+        ``ratios`` (B, max_inference_steps): Beta draws to inject when predict=False so that two implementations follow
+        one trajectory; when omitted the draws are made on the device (the reference calls ``beta_dist.sample()``, :569),
+        seeded from ``generator``.  ``return_velocities`` records the per-step CFG velocity (parity tests)."""
+        if prompt_embeds is None:
+            self.encode_prompt(prompt=prompt, negative_prompt=negative_prompt)
+        if guidance_scale is None:
+            raise ValueError("guidance_scale=None is unsupported (as in the reference, whose sigma.repeat(2) is unconditional, :526)")
+        if negative_prompt_embeds is None or negative_pooled_prompt_embeds is None or pooled_prompt_embeds is None:
+            raise ValueError("negative_prompt_embeds, pooled_prompt_embeds and negative_pooled_prompt_embeds are required")
+        device = self.device
+        batch_size = prompt_embeds.shape[0]
+        side = self.default_sample_size * self.vae_scale_factor
+        if latents is None:
+            latents = self.prepare_latents(batch_size, self.transformer.config.in_channels, side, side, prompt_embeds.dtype, device,
+                                           generator, None)
+        init_noise_latents = latents.clone()
+        if fix_sigmas is not None:
+            max_inference_steps = len(fix_sigmas[0])
+        seed = 0
+        if not predict and ratios is None:
+            gen = generator[0] if isinstance(generator, (list, tuple)) else generator
+            seed = int(gen.initial_seed()) if gen is not None else int(torch.randint(0, 2**31 - 1, (1,)).item())
+        eng = self.get_engine()
+        res = eng.sample(latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
+                         max_inference_steps, float(guidance_scale), bool(predict), ratios=ratios, seed=seed,
+                         record_tpm_inputs=not predict, record_velocity=return_velocities)
+        out_dtype = latents.dtype
+        prob_masks = res["prob_masks"]
+        logprobs = torch.masked_fill(res["logprobs_raw"], prob_masks, 1.0)          # INVALID_LOGPROB (:615-621)
+        hist = res["history_latents"]                                              # (B, T, C, h, w)
+        last_valid_indices = []
+        finals = []
+        for i in range(batch_size):                                                # :646-652
+            lv = torch.where(~prob_masks[i])[0][-1]
+            last_valid_indices.append(lv)
+            finals.append(hist[i, lv])
+        finals = torch.stack(finals).to(out_dtype)
+        images = []
+        if self.vae is not None and hasattr(self.vae, "decode"):                   # :645-655 (VAE is caller-supplied)
+            for i in range(batch_size):
+                lat = (finals[i] / self.vae.config.scaling_factor) + self.vae.config.shift_factor
+                images.append(self.vae.decode(lat.unsqueeze(0).to(self.vae.dtype), return_dict=False)[0].detach())
+        hcs = None
+        if "tpm_inputs_nhwc" in res:  # (B, T, g, g, 2D) bf16 -> reference layout (B, T, 2D, g, g) as a zero-copy view
+            hcs = res["tpm_inputs_nhwc"].permute(0, 1, 4, 2, 3)
+        out = CustomDiffusionModelOutput(
+            init_noise_latents=init_noise_latents, hidden_states_combineds=hcs, tembs=res["tembs"].to(out_dtype), images=images,
+            last_valid_indices=last_valid_indices, alphas=res["alphas"], betas=res["betas"], sigmas=res["sigmas"],
+            logprobs=logprobs, prob_masks=prob_masks, latents=finals)
+        if return_velocities:
+            out["velocities"] = res["velocities"]
+        return out
+
+    # ---------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def only_predict_logprobs(self, fix_sigmas: torch.Tensor, fix_hidden_states_combineds: torch.Tensor, fix_tembs: torch.Tensor):
+        """modeling_sd3_pnt.py:670-726 (forward replay; gradients w.r.t. the TPM are the next row of SURVEY section 8a)."""
+        if fix_sigmas is None:
+            raise ValueError("fix_sigmas must be provided")
+        if fix_hidden_states_combineds is None:
+            raise ValueError("fix_hidden_states_combineds must be provided")
+        eng = self.get_engine()
+        device = self.device
+        batch_size, steps = fix_sigmas.shape[:2]
+        fix_sigmas = fix_sigmas.to(device=device, dtype=torch.float32)
+        sigma = torch.ones(batch_size, dtype=torch.float32, device=device)
+        logprobs, masks = [], []
+        for step in range(steps):
+            ab = eng.tpm_forward(fix_hidden_states_combineds[:, step], fix_tembs[:, step])
+            alpha, beta = ab[:, 0], ab[:, 1]
+            if self.prediction_type == "mode_concentration":
+                alpha, beta = ab[:, 0] * (ab[:, 1] - 2) + 1, (1 - ab[:, 0]) * (ab[:, 1] - 2) + 1
+            sigma_next = fix_sigmas[:, step]
+            finished = sigma < self.min_sigma
+            ratio = sigma_next / sigma if self.relative else sigma - sigma_next
+            ratio = torch.clamp(torch.where(finished, torch.full_like(ratio, 0.5), ratio), min=self.epsilon, max=1 - self.epsilon)
+            lp = ((alpha - 1) * torch.log(ratio) + (beta - 1) * torch.log1p(-ratio)
+                  + torch.lgamma(alpha + beta) - torch.lgamma(alpha) - torch.lgamma(beta))
+            logprobs.append(torch.where(finished, torch.zeros_like(lp), lp))
+            masks.append(finished)
+            sigma = sigma_next
+        logprobs = torch.stack(logprobs, dim=1)
+        masks = torch.stack(masks, dim=1)
+        return {"logprobs": torch.masked_fill(logprobs, masks, 1.0)}
+
+
+class SD3PredictNextTimeStepModelRLOOWrapper(nn.Module):
+    """modeling_sd3_pnt.py:729-933: the surface CommonRLOOTrainer calls (rloo_trainer.py:432-485)."""
+
+    def __init__(
+        self,
+        pretrained_model_name_or_path=None,
+        torch_dtype: torch.dtype = torch.float16,
+        min_sigma: float = 0.01,
+        pre_process: bool = False,
+        init_alpha: float = 1.5,
+        init_beta: float = 0.5,
+        relative: bool = True,
+        prediction_type: str = "alpha_beta",
+        fsdp: str = [],
+        max_inference_steps: int = 28,
+        transformer_config: Optional[dict] = None,
+        device=None,
+    ):
+        super().__init__()
+        self.pretrained_model_name_or_path = pretrained_model_name_or_path or ""
+        self.agent_model = SD3PredictNextTimeStepModel(
+            pretrained_model_name_or_path, torch_dtype=torch_dtype, init_alpha=init_alpha, init_beta=init_beta, min_sigma=min_sigma,
+            pre_process=pre_process, relative=relative, prediction_type=prediction_type, transformer_config=transformer_config,
+            device=device).eval()
+        self.relative = relative
+        self.fsdp = fsdp
+        self.max_inference_steps = max_inference_steps
+        self.agent_model.requires_grad_(False)
+        self.agent_model.time_predictor.train()
+        self.agent_model.time_predictor.requires_grad_(True)
+
+    def rloo_repeat(self, data, rloo_k):
+        """:768-786"""
+        if "prompt" in data:
+            data["prompt"] = data["prompt"] * rloo_k
+        for key in ["prompt_embeds", "negative_prompt_embeds", "pooled_prompt_embeds", "negative_pooled_prompt_embeds"]:
+            if key in data:
+                size = [rloo_k] + [1] * (len(data[key].shape) - 1)
+                data[key] = data[key].repeat(*size)
+        return data
+
+    def sample(self, inputs):
+        """:788-806 (weights are replicated per GPU, so there is no FSDP summon)."""
+        if "3.5" in self.pretrained_model_name_or_path:
+            inputs["guidance_scale"] = 3.5
+        inputs["max_inference_steps"] = self.max_inference_steps
+        return self.agent_model(**{k: v for k, v in inputs.items() if k != "prompt" or "prompt_embeds" not in inputs})
+
+    def reward(self, inputs, outputs, reward_model, gamma=0.8, return_last_reward=False):
+        """:808-849.  ``reward_model.score(prompt, image)`` is caller-supplied (reward towers are out of scope); when the
+        pipeline has no VAE the final latent (C, h, w) is handed to it in place of the PIL image."""
+        prompts = inputs.get("prompt", None)
+        images = outputs.get("images", None)
+        prob_masks = outputs.get("prob_masks", None)
+        last_valid_indices = outputs.get("last_valid_indices", [])
+        if not images:
+            images = [[lat] for lat in outputs["latents"]]
+        if prompts is None or images is None:
+            raise ValueError("prompt and images must be provided")
+        elif len(prompts) != len(images):
+            raise ValueError("prompt and images must have the same length")
+        rewards, last_image_rewards = [], []
+        for i, (prompt, image, prob_mask) in enumerate(zip(prompts, images, prob_masks)):
+            if last_valid_indices == []:
+                last_image_idx = torch.where(~prob_mask.bool())[-1][-1].item()
+                last_image = image[last_image_idx]
+            else:
+                last_image_idx = int(last_valid_indices[i])
+                last_image = image[0]
+            last_image_reward = float(reward_model.score(prompt, last_image))
+            last_image_rewards.append(last_image_reward)
+            reward = 0
+            for j in range(last_image_idx + 1):
+                reward += last_image_reward * (gamma ** (last_image_idx - j))
+            rewards.append(reward / (last_image_idx + 1))
+        rewards, last_image_rewards = torch.tensor(rewards), torch.tensor(last_image_rewards)
+        return (rewards, last_image_rewards) if return_last_reward else rewards
+
+    def logprobs(self, inputs, outputs):
+        """:851-873"""
+        return self.agent_model.only_predict_logprobs(
+            fix_sigmas=outputs["sigmas"], fix_hidden_states_combineds=outputs["hidden_states_combineds"],
+            fix_tembs=outputs["tembs"])["logprobs"]
+
+    def kl_divergence(self, outputs: CustomDiffusionModelOutput):
+        """:875-901, vectorised: KL(Beta(alpha, beta) || reference Beta) per step, 0 where masked."""
+        alphas, betas, prob_masks = outputs["alphas"].float().cpu(), outputs["betas"].float().cpu(), outputs["prob_masks"].cpu()
+        input_sigmas = F.pad(outputs["sigmas"].float().cpu()[..., :-1], (1, 0), value=1.0)
+        if self.relative:
+            ref_a, ref_b = get_ref_beta(input_sigmas)
+        else:
+            ref_a, ref_b = torch.full_like(alphas, 1.4), torch.full_like(alphas, 11.2)
+        kl = torch.distributions.kl_divergence(torch.distributions.Beta(alphas, betas), torch.distributions.Beta(ref_a, ref_b))
+        return torch.where(prob_masks.bool(), torch.zeros_like(kl), kl)
+
+    def subset_inputs(self, inputs, micro_batch_inds):
+        """:903-914"""
+        subset = {}
+        for key, value in inputs.items():
+            if isinstance(value, torch.Tensor):
+                subset[key] = value[micro_batch_inds]
+            elif isinstance(value, list):
+                subset[key] = [value[i] for i in micro_batch_inds]
+            elif isinstance(value, (float, int)) or value is None:
+                subset[key] = value
+            else:
+                raise ValueError(f"Unsupported input type: {type(value)}")
+        return subset
+
+    def subset_outputs(self, outputs, micro_batch_inds):
+        """:916-933"""
+        subset = {}
+        for key, value in outputs.items():
+            if isinstance(value, torch.Tensor):
+                subset[key] = value[micro_batch_inds]
+            elif isinstance(value, list):
+                subset[key] = [value[i] for i in micro_batch_inds]
+            elif isinstance(value, dict):
+                subset[key] = {k: v[micro_batch_inds] for k, v in value.items() if isinstance(v, torch.Tensor)}
+            elif value is None:
+                subset[key] = None
+            else:
+                raise ValueError(f"Unsupported output type: {type(value)}")
+        return subset

@@ -47,7 +47,7 @@ def gemm_case(batch, rows, N, K, epi, time_it=False):
     st = lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gate), L.ptr(out), batch, rows, N, K, epi, None)
     torch.cuda.synchronize()
     msg = f"gemm b={batch} rows={rows} N={N} K={K} epi={epi}: status={st} rel={rel(out, ref):.3e} maxabs={float((out.float()-ref).abs().max()):.3e}"
-    if time_it and epi != 3:
+    if time_it:
         ms = timeit(lambda: lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), L.ptr(bias), L.ptr(gate), L.ptr(out), batch, rows, N, K, epi, None))
         msg += f"  {ms*1e3:.1f} us  {2*batch*rows*N*K/ms/1e9:.1f} TFLOP/s"
     print(msg, flush=True)
@@ -108,7 +108,9 @@ if __name__ == "__main__":
         gemm_case(2, 256, 64, 384, 1)
         gemm_case(2, 4096, 4608, 1536, 0, True)
         gemm_case(2, 4096, 6144, 1536, 2, True)
-        gemm_case(2, 4096, 1536, 6144, 3)
+        gemm_case(2, 4096, 1536, 6144, 3, True)
+        gemm_case(2, 4096, 1536, 1536, 3, True)
+        gemm_case(2, 333, 1536, 1536, 3, True)
         gemm_case(2, 4096, 1536, 6144, 1, True)
     if which in ("all", "conv"):
         conv_case(2, 16, 128, 128)
@@ -121,4 +123,11 @@ if __name__ == "__main__":
         attn_case(1, 1357, 4, 64)
         attn_case(1, 1357, 4, 64, q_rows=1024)
         attn_case(2, 4429, 24, 64, 0, True)
+    if which == "attn_big":
+        attn_case(2, 4429, 24, 64)
+        attn_case(2, 4429, 24, 64)
+    if which == "gemm_big":
+        gemm_case(2, 4096, 6144, 1536, 2)
+        gemm_case(2, 4096, 1536, 1536, 3)
+        gemm_case(2, 4096, 1536, 6144, 3)
     print("diag done", flush=True)

@@ -6,14 +6,19 @@
 // [Bt][S][3*H*dp] through 4-D TMA tensor maps (no head permute, no concat copy); O is written token-major [Bt][S][H*dp]
 // so the output projection consumes it as-is.
 //
-// One CTA = one 128-row query tile of one (batch, head); 256 threads; two CTAs are co-resident per SM (dp=64) so that
-// one CTA's softmax overlaps the other's MMAs:
-//   warp 0      TMA producer  (Q once, K/V tiles of 128 keys through a 2-stage ring)
-//   warp 1      MMA issuer    S = Q K^T (SS, 128x128xdp) -> TMEM;  O += P V (A = P from TMEM, B = V MN-major from smem)
+// One CTA = one 128-row query tile of one (batch, head); 256 threads; two CTAs co-resident per SM (dp = 64).
+//   warp 0      TMA producer  (Q once, K/V tiles of 128 keys through a 2-stage smem ring)
+//   warp 1      MMA issuer.  Keys are consumed in HALF-tiles of 64:  S[b] = Q K_half^T (SS, 128x64xdp) and
+//               O += P[b] V_half (A = P from TMEM, B = V MN-major from smem), b = half-tile parity
 //   warp 2      TMEM allocator
-//   warps 4-7   softmax: one thread per query row, fp32, exp2 with the log2(e)/sqrt(d) scale folded in, online max with
-//               lazy rescale (O in TMEM is only touched when the running max grows by more than 2^8), P written back to
-//               TMEM as packed bf16; final 1/l normalisation and bf16 store.
+//   warps 4-7   softmax, one thread per query row.
+// S and P are DOUBLE-BUFFERED in TMEM (S[2] 64 fp32 columns each, P[2] 32 packed-bf16 columns each, O dp columns), so the
+// softmax warps never wait for the tensor core in steady state: while they work on half-tile i the MMA warp has already
+// produced S(i+1) and is accumulating P(i-1) V.  The kernel is then bound by the MUFU ex2 rate, which is the d=64 limit.
+// Softmax: fp32, exp2 with log2(e)/sqrt(d) folded into one FFMA2, single pass per half-tile against a possibly stale
+// running max (exact: the final 1/l normalisation cancels it); when a half-tile raises the max by more than 2^8 the
+// accumulator O and the row sum are rescaled once the outstanding P V has drained; the first half-tile, the masked tail
+// and (never observed) jumps above 2^100 take an exact two-pass route.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -25,7 +30,8 @@ namespace {
 
 constexpr int kAttnThreads = 256;
 constexpr int kQT = 128;   // query rows per CTA
-constexpr int kKT = 128;   // keys per KV tile
+constexpr int kKT = 128;   // keys per K/V smem tile
+constexpr int kHT = 64;    // keys per half-tile (one S / P buffer)
 constexpr int kKVStages = 2;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
@@ -38,7 +44,9 @@ struct AttnSmem {
   static constexpr int kBarOff = kVOff + kKVStages * kTile;
   static constexpr int kTotal = kBarOff + 256 + 1024;
   static constexpr uint32_t kTmemCols = DP == 64 ? 256 : 512;
-  static constexpr uint32_t kSCol = 0, kPCol = 128, kOCol = 192;
+  static constexpr uint32_t kSCol = 0;     // S[b] at kSCol + 64 b
+  static constexpr uint32_t kPCol = 128;   // P[b] at kPCol + 32 b
+  static constexpr uint32_t kOCol = 192;   // O: DP columns
 };
 
 template <int DP>
@@ -53,17 +61,18 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   uint64_t* v_full = k_full + kKVStages;       // [kKVStages]
   uint64_t* k_empty = v_full + kKVStages;      // [kKVStages]
   uint64_t* v_empty = k_empty + kKVStages;     // [kKVStages]
-  uint64_t* s_full = v_empty + kKVStages;
-  uint64_t* s_empty = s_full + 1;
-  uint64_t* p_full = s_empty + 1;
-  uint64_t* pv_done = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+  uint64_t* s_full = v_empty + kKVStages;      // [2]  MMA -> softmax : S[b] written
+  uint64_t* s_free = s_full + 2;               // [2]  softmax -> MMA : S[b] read into registers
+  uint64_t* p_full = s_free + 2;               // [2]  softmax -> MMA : P[b] written (and O rescaled if needed)
+  uint64_t* pv_done = p_full + 2;              // [2]  MMA -> softmax : P[b] V accumulated (P[b] may be overwritten)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * kQT;
   const int n_kv = (A.S + kKT - 1) / kKT;
+  const int n_half = (A.S + kHT - 1) / kHT;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&A.tmQ);
@@ -78,10 +87,12 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
-    mbar_init(p_full, 4);
-    mbar_init(pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -120,152 +131,200 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, false);
+    constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kHT, false);
     constexpr uint32_t idesc_pv = make_idesc_bf16(kQT, DP, true);
-    const uint32_t s_tmem = tmem_base + L::kSCol, p_tmem = tmem_base + L::kPCol, o_tmem = tmem_base + L::kOCol;
     const uint32_t q_base = smem_u32(smem + L::kQOff);
 
-    auto issue_qk = [&](int stage) {
-      const uint32_t k_base = smem_u32(smem + L::kKOff + stage * L::kTile);
+    // half-tile i lives in K/V smem tile t = i/2 (ring stage t % 2, ring phase (t/2) & 1), rows [64 (i&1), +64)
+    auto issue_qk = [&](int i) {
+      const int t = i >> 1, hf = i & 1, stage = t % kKVStages;
+      if (hf == 0) mbar_wait(&k_full[stage], (t / kKVStages) & 1);
+      if (i >= 2) mbar_wait(&s_free[i & 1], ((i - 2) >> 1) & 1);  // softmax(i-2) has read S[i&1]
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t k_base = smem_u32(smem + L::kKOff + stage * L::kTile) + hf * (kHT * 128);
+        const uint32_t s_tmem = tmem_base + L::kSCol + (i & 1) * kHT;
 #pragma unroll
-      for (int ks = 0; ks < DP / 16; ++ks) {
-        const uint32_t off = (ks / 4) * (kQT * 128) + (ks % 4) * 32;
-        umma_ss(s_tmem, make_smem_desc_sw128(q_base + off, 16, 1024), make_smem_desc_sw128(k_base + off, 16, 1024), idesc_qk,
-                ks != 0 ? 1u : 0u);
+        for (int ks = 0; ks < DP / 16; ++ks) {
+          const uint32_t off = (ks / 4) * (kQT * 128) + (ks % 4) * 32;
+          umma_ss(s_tmem, make_smem_desc_sw128(q_base + off, 16, 1024), make_smem_desc_sw128(k_base + off, 16, 1024), idesc_qk,
+                  ks != 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[i & 1]);
+        if (hf == 1 || i == n_half - 1) umma_commit(&k_empty[stage]);
       }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int i) {
+      const int t = i >> 1, hf = i & 1, stage = t % kKVStages;
+      mbar_wait(&p_full[i & 1], (i >> 1) & 1);
+      if (hf == 0) mbar_wait(&v_full[stage], (t / kKVStages) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t v_base = smem_u32(smem + L::kVOff + stage * L::kTile) + hf * (kHT * 128);
+        const uint32_t p_tmem = tmem_base + L::kPCol + (i & 1) * (kHT / 2);
+        const uint32_t o_tmem = tmem_base + L::kOCol;
+#pragma unroll
+        for (int ks = 0; ks < kHT / 16; ++ks) {
+          // B = V half-tile, MN-major: 16 keys per MMA = 16 rows of 128 B; 64-wide d-groups are kKT*128 B apart (LBO)
+          umma_ts(o_tmem, p_tmem + ks * 8, make_smem_desc_sw128(v_base + ks * 2048, kKT * 128, 1024), idesc_pv,
+                  (i | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(&pv_done[i & 1]);
+        if (hf == 1 || i == n_half - 1) umma_commit(&v_empty[stage]);
+      }
+      __syncwarp();
     };
 
     mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    if (lane == 0) {
-      issue_qk(0);
-      umma_commit(&k_empty[0]);
-      umma_commit(s_full);
-    }
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      int nstage = stage + 1;
-      uint32_t nphase = phase;
-      if (nstage == kKVStages) {
-        nstage = 0;
-        nphase ^= 1;
-      }
-      if (j + 1 < n_kv) {
-        mbar_wait(&k_full[nstage], nphase);
-        mbar_wait(s_empty, j & 1);  // softmax has read S_j
-        tc_fence_after();
-        if (lane == 0) {
-          issue_qk(nstage);
-          umma_commit(&k_empty[nstage]);
-          umma_commit(s_full);
-        }
-        __syncwarp();
-      }
-      mbar_wait(p_full, j & 1);  // P_j in TMEM, O corrected
-      mbar_wait(&v_full[stage], phase);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t v_base = smem_u32(smem + L::kVOff + stage * L::kTile);
-#pragma unroll
-        for (int ks = 0; ks < kKT / 16; ++ks) {
-          // B = V tile, MN-major: 16 keys per MMA = 16 rows of 128 B; 64-wide d-groups are kKT*128 B apart (LBO)
-          umma_ts(o_tmem, p_tmem + ks * 8, make_smem_desc_sw128(v_base + ks * 2048, kKT * 128, 1024), idesc_pv,
-                  (j | ks) != 0 ? 1u : 0u);
-        }
-        umma_commit(&v_empty[stage]);
-        umma_commit(pv_done);
-      }
-      __syncwarp();
-      stage = nstage;
-      phase = nphase;
+    issue_qk(0);
+    for (int i = 0; i < n_half; ++i) {
+      if (i + 1 < n_half) issue_qk(i + 1);
+      issue_pv(i);
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- softmax / correction / epilogue
     const int q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t s_tmem = tmem_base + lane_off + L::kSCol;
-    const uint32_t p_tmem = tmem_base + lane_off + L::kPCol;
     const uint32_t o_tmem = tmem_base + lane_off + L::kOCol;
     const float scale = A.scale_log2;
-    float m_used = -INFINITY;  // running (possibly stale) max, log2 domain
-    float l = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int valid = A.S - j * kKT;  // keys valid in this tile (>=1)
-      mbar_wait(s_full, j & 1);
+    const uint64_t scale2 = pack_f32x2(scale, scale);
+    float m_used = -INFINITY;            // reference max of the running sums (log2 domain); may lag the true max
+    uint64_t l2 = pack_f32x2(0.f, 0.f);  // row sum as two partial sums
+    float alpha_pending = 1.f;           // rescale discovered in half-tile i-1, applied before P(i) is published
+    bool need_pending = false;
+
+    auto rescale_o = [&](float alpha) {
+#pragma unroll
+      for (int c = 0; c < DP / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32(o_tmem + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x32(o_tmem + c * 32, o);
+      }
+      l2 = fmul2(l2, pack_f32x2(alpha, alpha));
+    };
+    // p = exp2(s * scale - m) for one 32-column chunk, packed to bf16 into P; accumulates the row sum
+    auto exp_chunk = [&](const uint32_t (&v)[32], uint32_t p_dst, uint64_t negm2) {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float x0, x1;
+        unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), scale2, negm2), x0, x1);
+        const float p0 = exp2_approx(x0), p1 = exp2_approx(x1);
+        l2 = fadd2(l2, pack_f32x2(p0, p1));
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+      tmem_st_32x16(p_dst, pk);
+    };
+    auto chunk_max = [&](const uint32_t (&v)[32], float m) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) m = fmax3(m, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+      return m;
+    };
+
+    for (int i = 0; i < n_half; ++i) {
+      const int bb = i & 1;
+      const uint32_t s_tmem = tmem_base + lane_off + L::kSCol + bb * kHT;
+      const uint32_t p_tmem = tmem_base + lane_off + L::kPCol + bb * (kHT / 2);
+      const int valid = A.S - i * kHT;  // keys valid in this half-tile (>= 1)
+      mbar_wait(&s_full[bb], (i >> 1) & 1);
+      if (i >= 2) mbar_wait(&pv_done[bb], ((i - 2) >> 1) & 1);  // P(i-2) V done: P[bb] may be overwritten
       tc_fence_after();
-      // pass 1: row max
-      float m_tile = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < kKT / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_tmem + c * 32, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (c * 32 + i >= valid) s = -INFINITY;
-          m_tile = fmaxf(m_tile, s);
-        }
-      }
-      m_tile *= scale;
-      float alpha = 1.f;
-      bool need = false;
-      if (j == 0) {
-        m_used = m_tile;
-      } else if (m_tile > m_used + kRescaleThreshold) {
-        need = true;
-        alpha = exp2_approx(m_used - m_tile);
-        m_used = m_tile;
-      }
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // PV_{j-1} finished: P and O may be touched
+      if (__any_sync(0xffffffffu, need_pending)) {
+        // every P V issued so far must have drained before O is touched (P(i-1) V is the newest; the MMAs retire in order)
+        mbar_wait(&pv_done[bb ^ 1], ((i - 1) >> 1) & 1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, need)) {
-#pragma unroll
-          for (int c = 0; c < DP / 32; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(o_tmem + c * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(o_tmem + c * 32, o);
-          }
-          l *= alpha;
-        }
+        rescale_o(alpha_pending);
       }
-      // pass 2: p = exp2(s*scale - m), row sum, bf16 P -> TMEM
-#pragma unroll
-      for (int c = 0; c < kKT / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(s_tmem + c * 32, v);
+      need_pending = false;
+      alpha_pending = 1.f;
+      bool fast_ok = false;
+      if (i > 0 && valid >= kHT) {
+        // ---- fast path: one pass with the (possibly stale) running max; the half-tile's own max is tracked on the side
+        const uint64_t l_save = l2;
+        const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
+        uint32_t va[32], vb[32];
+        tmem_ld_32x32(s_tmem, va);
         tmem_wait_ld();
-        if (c == kKT / 32 - 1) {
+        tmem_ld_32x32(s_tmem + 32, vb);
+        float tmax = chunk_max(va, -INFINITY);
+        exp_chunk(va, p_tmem, negm2);
+        tmem_wait_ld();
+        tmax = chunk_max(vb, tmax);
+        const float grow = tmax * scale - m_used;
+        if (!__any_sync(0xffffffffu, grow > 100.f)) {  // exp2 cannot overflow: accept
+          fast_ok = true;
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(s_empty);
+          if (lane == 0) mbar_arrive(&s_free[bb]);
+          exp_chunk(vb, p_tmem + 16, negm2);
+          if (grow > kRescaleThreshold) {
+            need_pending = true;
+            alpha_pending = exp2_approx(-grow);
+            m_used = tmax * scale;
+          }
+        } else {
+          l2 = l_save;  // S[bb] is still intact (s_free not signalled): redo on the exact route
         }
-        uint32_t pk[16];
+      }
+      if (!fast_ok) {
+        // ---- exact two-pass route: first half-tile, masked tail, or a jump of the row max above 2^100
+        float m_tile = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2_approx(fmaf(__uint_as_float(v[i]), scale, -m_used));
-          float p1 = exp2_approx(fmaf(__uint_as_float(v[i + 1]), scale, -m_used));
-          if (c * 32 + i >= valid) p0 = 0.f;
-          if (c * 32 + i + 1 >= valid) p1 = 0.f;
-          l += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
+        for (int c = 0; c < kHT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_tmem + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            float sv = __uint_as_float(v[e]);
+            if (c * 32 + e >= valid) sv = -INFINITY;
+            m_tile = fmaxf(m_tile, sv);
+          }
         }
-        tmem_st_32x16(p_tmem + c * 16, pk);
+        m_tile *= scale;
+        if (i == 0) {
+          m_used = m_tile;
+        } else {
+          const bool need = m_tile > m_used + kRescaleThreshold;
+          const float alpha = need ? exp2_approx(m_used - m_tile) : 1.f;
+          if (need) m_used = m_tile;
+          if (__any_sync(0xffffffffu, need)) {
+            mbar_wait(&pv_done[bb ^ 1], ((i - 1) >> 1) & 1);
+            tc_fence_after();
+            rescale_o(alpha);
+          }
+        }
+        const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
+#pragma unroll
+        for (int c = 0; c < kHT / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_tmem + c * 32, v);
+          tmem_wait_ld();
+          if (c == kHT / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_free[bb]);
+          }
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e >= valid) v[e] = 0xff800000u;  // -inf -> p = 0
+          exp_chunk(v, p_tmem + c * 16, negm2);
+        }
       }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[bb]);
     }
+    float l_lo, l_hi;
+    unpack_f32x2(l2, l_lo, l_hi);
+    const float l = l_lo + l_hi;
     // epilogue: O / l -> bf16, token-major
-    mbar_wait(pv_done, (n_kv - 1) & 1);
+    mbar_wait(&pv_done[(n_half - 1) & 1], ((n_half - 1) >> 1) & 1);
     tc_fence_after();
     const int row = q0 + q * 32 + lane;
     const float inv_l = 1.0f / l;
@@ -278,13 +337,13 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       if (row < A.S) {
         uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int e = 0; e < 4; ++e) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * i + 0]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l);
-          w.y = pack_bf16x2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l);
-          w.z = pack_bf16x2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l);
-          w.w = pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l);
-          dst[i] = w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * e + 0]) * inv_l, __uint_as_float(o[8 * e + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv_l, __uint_as_float(o[8 * e + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv_l, __uint_as_float(o[8 * e + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv_l, __uint_as_float(o[8 * e + 7]) * inv_l);
+          dst[e] = w;
         }
       }
     }

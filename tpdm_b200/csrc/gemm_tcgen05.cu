@@ -189,7 +189,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       n_chunks = n_chunks > BN / 32 ? BN / 32 : n_chunks;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
+      int rows = G.rows_per_batch - row_base;
+      rows = rows > 32 ? 32 : rows;
+      const float* gate_row = G.epi == EPI_GATE_RESIDUAL ? G.gate + static_cast<long long>(tc.b) * G.gate_stride : nullptr;
       for (int c = 0; c < n_chunks; ++c) {
+        const int col = n0 + c * 32 + lane;
+        const bool col_ok = col < G.N && rows > 0;
+        const long long o0 = static_cast<long long>(tc.b) * G.out_batch_stride + static_cast<long long>(row_base) * G.ldo + col;
+        const float bias = (col_ok && G.bias) ? G.bias[col] : 0.f;
+        // residual mode: the read half of the read-modify-write does not depend on the accumulator -- issue all 32 row
+        // loads (row-contiguous, 128 B per warp) before waiting on TMEM so their latency overlaps the MMA tail
+        float resv[32];
+        float gate = 0.f;
+        if (G.epi == EPI_GATE_RESIDUAL && col_ok) {
+          const float* o = reinterpret_cast<const float*>(G.out) + o0;
+          gate = gate_row[col];
+#pragma unroll
+          for (int r = 0; r < 32; ++r) resv[r] = r < rows ? o[static_cast<long long>(r) * G.ldo] : 0.f;
+        }
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
         tmem_wait_ld();
@@ -201,30 +218,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
 #pragma unroll
         for (int j = 0; j < 32; ++j) st[lane * kStagePad + j] = __uint_as_float(v[j]);
         __syncwarp();
-        const int col = n0 + c * 32 + lane;
-        const bool col_ok = col < G.N;
-        const float bias = (col_ok && G.bias) ? G.bias[col] : 0.f;
-        int rows = G.rows_per_batch - row_base;
-        rows = rows > 32 ? 32 : rows;
-        if (col_ok && rows > 0) {
-          const long long o0 = static_cast<long long>(tc.b) * G.out_batch_stride + static_cast<long long>(row_base) * G.ldo + col;
+        if (col_ok) {
           if (G.epi == EPI_BIAS_BF16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + o0;
-            for (int r = 0; r < rows; ++r) o[static_cast<long long>(r) * G.ldo] = __float2bfloat16(st[r * kStagePad + lane] + bias);
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < rows) o[static_cast<long long>(r) * G.ldo] = __float2bfloat16(st[r * kStagePad + lane] + bias);
           } else if (G.epi == EPI_BIAS_GELU_BF16) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + o0;
-            for (int r = 0; r < rows; ++r)
-              o[static_cast<long long>(r) * G.ldo] = __float2bfloat16(gelu_tanh(st[r * kStagePad + lane] + bias));
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < rows) o[static_cast<long long>(r) * G.ldo] = __float2bfloat16(gelu_tanh(st[r * kStagePad + lane] + bias));
           } else if (G.epi == EPI_BIAS_F32) {
             float* o = reinterpret_cast<float*>(G.out) + o0;
-            for (int r = 0; r < rows; ++r) o[static_cast<long long>(r) * G.ldo] = st[r * kStagePad + lane] + bias;
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < rows) o[static_cast<long long>(r) * G.ldo] = st[r * kStagePad + lane] + bias;
           } else {  // EPI_GATE_RESIDUAL
             float* o = reinterpret_cast<float*>(G.out) + o0;
-            const float gate = G.gate[static_cast<long long>(tc.b) * G.gate_stride + col];
-            for (int r = 0; r < rows; ++r) {
-              float* p = o + static_cast<long long>(r) * G.ldo;
-              *p = *p + gate * (st[r * kStagePad + lane] + bias);
-            }
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              if (r < rows) o[static_cast<long long>(r) * G.ldo] = resv[r] + gate * (st[r * kStagePad + lane] + bias);
           }
         }
         __syncwarp();

@@ -27,7 +27,7 @@ constexpr int BK = 64;
 constexpr int kStages = 4;
 constexpr int kGemmThreads = 192;
 constexpr int kABytes = BM * BK * 2;
-constexpr int kStagePad = 33;  // floats per staged row
+constexpr int kStagePad = 36;  // floats per staged row: 16-byte aligned rows, conflict-free 128-bit access
 
 struct GemmParams {
   GemmOp op[2];
@@ -191,21 +191,42 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       tc_fence_after();
       int rows = G.rows_per_batch - row_base;
       rows = rows > 32 ? 32 : rows;
+      const bool f32_out = G.epi == EPI_BIAS_F32 || G.epi == EPI_GATE_RESIDUAL;
+      // Row-contiguous 16-byte global accesses: a lane owns `vec` consecutive columns (8 bf16 / 4 fp32) of one row, so a
+      // warp-wide store covers whole 64 B / 128 B row segments instead of 2 bytes per lane.
+      const int vec = f32_out ? 4 : 8;
+      const int groups = 32 / vec;            // column groups per 32-column chunk
+      const int cg = lane % groups;           // this lane's column group
+      const int r_in = lane / groups;         // this lane's row within a pass
+      const int rows_per_pass = 32 / groups;  // 4 (bf16) or 8 (fp32) ... passes = 32 / rows_per_pass
       const float* gate_row = G.epi == EPI_GATE_RESIDUAL ? G.gate + static_cast<long long>(tc.b) * G.gate_stride : nullptr;
       for (int c = 0; c < n_chunks; ++c) {
-        const int col = n0 + c * 32 + lane;
+        const int col = n0 + c * 32 + cg * vec;
         const bool col_ok = col < G.N && rows > 0;
         const long long o0 = static_cast<long long>(tc.b) * G.out_batch_stride + static_cast<long long>(row_base) * G.ldo + col;
-        const float bias = (col_ok && G.bias) ? G.bias[col] : 0.f;
-        // residual mode: the read half of the read-modify-write does not depend on the accumulator -- issue all 32 row
-        // loads (row-contiguous, 128 B per warp) before waiting on TMEM so their latency overlaps the MMA tail
-        float resv[32];
-        float gate = 0.f;
-        if (G.epi == EPI_GATE_RESIDUAL && col_ok) {
-          const float* o = reinterpret_cast<const float*>(G.out) + o0;
-          gate = gate_row[col];
+        float bias[8], gate[4];
 #pragma unroll
-          for (int r = 0; r < 32; ++r) resv[r] = r < rows ? o[static_cast<long long>(r) * G.ldo] : 0.f;
+        for (int e = 0; e < 8; ++e) bias[e] = 0.f;
+        if (col_ok && G.bias) {
+          const float4 b0 = *reinterpret_cast<const float4*>(G.bias + col);
+          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+          if (!f32_out) {
+            const float4 b1 = *reinterpret_cast<const float4*>(G.bias + col + 4);
+            bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+          }
+        }
+        // residual mode: the read half of the read-modify-write does not depend on the accumulator -- issue all row loads
+        // before waiting on TMEM so their latency overlaps the MMA tail
+        float4 resv[8];
+        if (G.epi == EPI_GATE_RESIDUAL && col_ok) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gate_row + col);
+          gate[0] = g4.x; gate[1] = g4.y; gate[2] = g4.z; gate[3] = g4.w;
+          const float* o = reinterpret_cast<const float*>(G.out) + o0;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_in;
+            resv[it] = r < rows ? *reinterpret_cast<const float4*>(o + static_cast<long long>(r) * G.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
@@ -216,29 +237,48 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) st[lane * kStagePad + j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(st + lane * kStagePad + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         if (col_ok) {
-          if (G.epi == EPI_BIAS_BF16) {
+          if (!f32_out) {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + o0;
+            const bool gelu = G.epi == EPI_BIAS_GELU_BF16;
 #pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (r < rows) o[static_cast<long long>(r) * G.ldo] = __float2bfloat16(st[r * kStagePad + lane] + bias);
-          } else if (G.epi == EPI_BIAS_GELU_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + o0;
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + r_in;
+              if (r < rows) {
+                const float4 x0 = *reinterpret_cast<const float4*>(st + r * kStagePad + cg * 8);
+                const float4 x1 = *reinterpret_cast<const float4*>(st + r * kStagePad + cg * 8 + 4);
+                float y[8] = {x0.x + bias[0], x0.y + bias[1], x0.z + bias[2], x0.w + bias[3],
+                              x1.x + bias[4], x1.y + bias[5], x1.z + bias[6], x1.w + bias[7]};
+                if (gelu) {
 #pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (r < rows) o[static_cast<long long>(r) * G.ldo] = __float2bfloat16(gelu_tanh(st[r * kStagePad + lane] + bias));
-          } else if (G.epi == EPI_BIAS_F32) {
+                  for (int e = 0; e < 8; ++e) y[e] = gelu_tanh(y[e]);
+                }
+                uint4 w;
+                w.x = pack_bf16x2(y[0], y[1]);
+                w.y = pack_bf16x2(y[2], y[3]);
+                w.z = pack_bf16x2(y[4], y[5]);
+                w.w = pack_bf16x2(y[6], y[7]);
+                *reinterpret_cast<uint4*>(o + static_cast<long long>(r) * G.ldo) = w;
+              }
+            }
+          } else {
             float* o = reinterpret_cast<float*>(G.out) + o0;
+            const bool resid = G.epi == EPI_GATE_RESIDUAL;
 #pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (r < rows) o[static_cast<long long>(r) * G.ldo] = st[r * kStagePad + lane] + bias;
-          } else {  // EPI_GATE_RESIDUAL
-            float* o = reinterpret_cast<float*>(G.out) + o0;
-#pragma unroll
-            for (int r = 0; r < 32; ++r)
-              if (r < rows) o[static_cast<long long>(r) * G.ldo] = resv[r] + gate * (st[r * kStagePad + lane] + bias);
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + r_in;
+              if (r < rows) {
+                const float4 x = *reinterpret_cast<const float4*>(st + r * kStagePad + cg * 4);
+                float4 y = make_float4(x.x + bias[0], x.y + bias[1], x.z + bias[2], x.w + bias[3]);
+                if (resid)
+                  y = make_float4(resv[it].x + gate[0] * y.x, resv[it].y + gate[1] * y.y, resv[it].z + gate[2] * y.z,
+                                  resv[it].w + gate[3] * y.w);
+                *reinterpret_cast<float4*>(o + static_cast<long long>(r) * G.ldo) = y;
+              }
+            }
           }
         }
         __syncwarp();
@@ -290,6 +330,10 @@ int finish_op(GemmOp* op, const void* W, int N, int K, int epi, void* out, long 
   op->gate = gate;
   op->gate_stride = gate_stride;
   TPDM_CHECK(K % 8 == 0, TPDM_ERR_SHAPE, "gemm: K=%d must be a multiple of 8", K);
+  TPDM_CHECK(N % 8 == 0 && ldo % 8 == 0, TPDM_ERR_SHAPE, "gemm: N=%d and ldo=%d must be multiples of 8 (16-byte row segments)", N, ldo);
+  TPDM_CHECK((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(gate) & 15) == 0 && gate_stride % 4 == 0,
+             TPDM_ERR_ARG, "gemm: out / bias / gate must be 16-byte aligned");
   TPDM_CHECK(epi != EPI_GATE_RESIDUAL || gate != nullptr, TPDM_ERR_ARG, "gemm: gate pointer required");
   uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
   uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};

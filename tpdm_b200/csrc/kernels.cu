@@ -58,85 +58,108 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, int t_str
 // GEMV family: adaLN modulation linears of all blocks in one launch, time/text embedders, TPM norm1.linear
 // (diffusers AdaLayerNormZero/Continuous .linear, TimestepEmbedding, PixArtAlphaTextProjection; K6/K4 of SURVEY 2.2)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kGemvNB = 8;         // batch rows held per pass
 constexpr int kGemvRowsPerWarp = 4;
 constexpr int kGemvWarps = 8;
 
-template <typename WT>
+// One warp owns kGemvRowsPerWarp consecutive weight rows and streams them TOGETHER (4 independent 16-byte loads per lane
+// and k-step, unrolled x2 -> 8 loads in flight per lane) so HBM latency is covered by memory-level parallelism rather
+// than occupancy.  act(x) for NB batch rows is staged once per block in shared memory.
+template <typename WT, int NB>
 __global__ void __launch_bounds__(kGemvWarps * 32) gemv_kernel(const WT* __restrict__ W, const float* __restrict__ bias,
                                                                 const float* __restrict__ x, int ldx,
                                                                 const float* __restrict__ addend, float* __restrict__ y, int ldy,
                                                                 int Bt, int J, int K, int act) {
-  extern __shared__ float xs[];  // [nb][K]
+  extern __shared__ float xs[];  // [NB][K]
+  constexpr int EPL = 16 / sizeof(WT);  // elements per 16-byte load
+  constexpr int R = kGemvRowsPerWarp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j0 = (blockIdx.x * kGemvWarps + warp) * kGemvRowsPerWarp;
-  for (int b0 = 0; b0 < Bt; b0 += kGemvNB) {
-    const int nb = min(kGemvNB, Bt - b0);
+  const int j0 = (blockIdx.x * kGemvWarps + warp) * R;
+  for (int b0 = 0; b0 < Bt; b0 += NB) {
+    const int nb = min(NB, Bt - b0);
     __syncthreads();
-    for (int i = threadIdx.x; i < nb * K; i += blockDim.x) {
+    for (int i = threadIdx.x; i < NB * K; i += blockDim.x) {
       const int bb = i / K, k = i - bb * K;
-      float v = x[static_cast<long long>(b0 + bb) * ldx + k];
+      float v = bb < nb ? x[static_cast<long long>(b0 + bb) * ldx + k] : 0.f;
       xs[i] = act ? silu_f(v) : v;
     }
     __syncthreads();
-    for (int r = 0; r < kGemvRowsPerWarp; ++r) {
-      const int j = j0 + r;
-      if (j >= J) break;
-      float acc[kGemvNB];
+    if (j0 >= J) continue;
+    float acc[R][NB];
 #pragma unroll
-      for (int bb = 0; bb < kGemvNB; ++bb) acc[bb] = 0.f;
-      const WT* wrow = W + static_cast<long long>(j) * K;
-      constexpr int EPL = 16 / sizeof(WT);  // elements per 16-byte load
-      for (int k = lane * EPL; k < K; k += 32 * EPL) {
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int bb = 0; bb < NB; ++bb) acc[r][bb] = 0.f;
+    const WT* wrow[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) wrow[r] = W + static_cast<long long>(min(j0 + r, J - 1)) * K;
+#pragma unroll 2
+    for (int k = lane * EPL; k < K; k += 32 * EPL) {
+      uint4 raw[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) raw[r] = ldg_nc_u4(wrow[r] + k);
+      float xv[NB][EPL];
+#pragma unroll
+      for (int bb = 0; bb < NB; ++bb)
+#pragma unroll
+        for (int e = 0; e < EPL; e += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(xs + bb * K + k + e);
+          xv[bb][e] = t.x; xv[bb][e + 1] = t.y; xv[bb][e + 2] = t.z; xv[bb][e + 3] = t.w;
+        }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
         float w[EPL];
-        const uint4 raw = ldg_nc_u4(wrow + k);
         if constexpr (sizeof(WT) == 2) {
-          w[0] = bf16lo(raw.x); w[1] = bf16hi(raw.x); w[2] = bf16lo(raw.y); w[3] = bf16hi(raw.y);
-          w[4] = bf16lo(raw.z); w[5] = bf16hi(raw.z); w[6] = bf16lo(raw.w); w[7] = bf16hi(raw.w);
+          w[0] = bf16lo(raw[r].x); w[1] = bf16hi(raw[r].x); w[2] = bf16lo(raw[r].y); w[3] = bf16hi(raw[r].y);
+          w[4] = bf16lo(raw[r].z); w[5] = bf16hi(raw[r].z); w[6] = bf16lo(raw[r].w); w[7] = bf16hi(raw[r].w);
         } else {
-          w[0] = __uint_as_float(raw.x); w[1] = __uint_as_float(raw.y); w[2] = __uint_as_float(raw.z); w[3] = __uint_as_float(raw.w);
+          w[0] = __uint_as_float(raw[r].x); w[1] = __uint_as_float(raw[r].y); w[2] = __uint_as_float(raw[r].z);
+          w[3] = __uint_as_float(raw[r].w);
         }
 #pragma unroll
-        for (int bb = 0; bb < kGemvNB; ++bb) {
-          if (bb < nb) {
-            const float* xp = xs + bb * K + k;
+        for (int bb = 0; bb < NB; ++bb)
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) acc[bb] = fmaf(w[e], xp[e], acc[bb]);
-          }
-        }
-      }
-#pragma unroll
-      for (int bb = 0; bb < kGemvNB; ++bb) {
-        if (bb < nb) {
-          const float s = warp_sum(acc[bb]);
-          if (lane == 0) {
-            const long long o = static_cast<long long>(b0 + bb) * ldy + j;
-            y[o] = s + (bias ? bias[j] : 0.f) + (addend ? addend[o] : 0.f);
-          }
-        }
+          for (int e = 0; e < EPL; ++e) acc[r][bb] = fmaf(w[e], xv[bb][e], acc[r][bb]);
       }
     }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int bb = 0; bb < NB; ++bb) {
+        const float sum = warp_sum(acc[r][bb]);
+        const int j = j0 + r;
+        if (lane == 0 && j < J && bb < nb) {
+          const long long o = static_cast<long long>(b0 + bb) * ldy + j;
+          y[o] = sum + (bias ? bias[j] : 0.f) + (addend ? addend[o] : 0.f);
+        }
+      }
   }
+}
+
+template <typename WT, int NB>
+int gemv_launch_nb(const WT* W, const float* bias, const float* x, int ldx, const float* addend, float* y, int ldy, int Bt, int J, int K,
+                   int act, cudaStream_t s) {
+  const size_t smem = static_cast<size_t>(NB) * K * sizeof(float);
+  TPDM_CHECK(smem <= 160 * 1024, TPDM_ERR_SHAPE, "gemv: K=%d too large", K);
+  static bool attr_set = false;
+  if (smem > 48 * 1024 && !attr_set) {
+    TPDM_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<WT, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  const int rows_per_block = kGemvWarps * kGemvRowsPerWarp;
+  gemv_kernel<WT, NB><<<(J + rows_per_block - 1) / rows_per_block, kGemvWarps * 32, smem, s>>>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act);
+  count_launch();
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 template <typename WT>
 int gemv_launch(const WT* W, const float* bias, const float* x, int ldx, const float* addend, float* y, int ldy, int Bt, int J, int K,
                 int act, cudaStream_t s) {
   constexpr int EPL = 16 / sizeof(WT);
-  TPDM_CHECK(K % EPL == 0, TPDM_ERR_SHAPE, "gemv: K=%d must be a multiple of %d", K, EPL);
-  const int nb = Bt < kGemvNB ? Bt : kGemvNB;
-  const size_t smem = static_cast<size_t>(nb) * K * sizeof(float);
-  TPDM_CHECK(smem <= 160 * 1024, TPDM_ERR_SHAPE, "gemv: K=%d too large", K);
-  static size_t smem_set = 0;
-  if (smem > 48 * 1024 && smem > smem_set) {
-    TPDM_CUDA_OK(cudaFuncSetAttribute(gemv_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    smem_set = 160 * 1024;
-  }
-  const int rows_per_block = kGemvWarps * kGemvRowsPerWarp;
-  gemv_kernel<WT><<<(J + rows_per_block - 1) / rows_per_block, kGemvWarps * 32, smem, s>>>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act);
-  count_launch();
-  TPDM_CUDA_OK(cudaGetLastError());
-  return 0;
+  TPDM_CHECK(K % EPL == 0 && K % 4 == 0, TPDM_ERR_SHAPE, "gemv: K=%d must be a multiple of %d", K, EPL);
+  if (Bt <= 2) return gemv_launch_nb<WT, 2>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act, s);
+  if (Bt <= 4) return gemv_launch_nb<WT, 4>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act, s);
+  return gemv_launch_nb<WT, 8>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act, s);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -216,7 +239,10 @@ struct LnParams {
   const int* skip;
 };
 
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const LnParams P) {
+// VPL = float4 per lane (D = 128 * VPL): the row is read from global memory ONCE and kept in registers; VPL = 0 is the
+// generic three-pass route (statistics re-read through L1).
+template <int VPL>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant__ LnParams P) {
   if (P.skip != nullptr && *P.skip != 0) return;
   const int lane = threadIdx.x & 31;
   const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -226,17 +252,44 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const LnParams P) {
   const long long lr = r - (si ? P.rows0 : 0);
   const int b = static_cast<int>(lr / S.rows);
   const float* row = S.x + lr * P.D;
-  float mean, rstd;
-  row_stats(row, P.D, lane, mean, rstd);
   const float* sh = S.shift + static_cast<long long>(b) * S.mod_stride;
   const float* sc = S.scale + static_cast<long long>(b) * S.mod_stride;
   bf16* o = S.out + lr * P.D;
-  for (int k = lane * 4; k < P.D; k += 128) {
-    const float4 v = ld4(row + k), h = ld4(sh + k), c = ld4(sc + k);
-    uint2 w;
-    w.x = pack_bf16x2((v.x - mean) * rstd * (1.f + c.x) + h.x, (v.y - mean) * rstd * (1.f + c.y) + h.y);
-    w.y = pack_bf16x2((v.z - mean) * rstd * (1.f + c.z) + h.z, (v.w - mean) * rstd * (1.f + c.w) + h.w);
-    *reinterpret_cast<uint2*>(o + k) = w;
+  if constexpr (VPL > 0) {
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i] = ld4(row + (i * 32 + lane) * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / P.D;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + bq * bq) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / P.D + 1e-6f);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int k = (i * 32 + lane) * 4;
+      const float4 h = ld4(sh + k), c = ld4(sc + k);
+      uint2 w;
+      w.x = pack_bf16x2((v[i].x - mean) * rstd * (1.f + c.x) + h.x, (v[i].y - mean) * rstd * (1.f + c.y) + h.y);
+      w.y = pack_bf16x2((v[i].z - mean) * rstd * (1.f + c.z) + h.z, (v[i].w - mean) * rstd * (1.f + c.w) + h.w);
+      *reinterpret_cast<uint2*>(o + k) = w;
+    }
+  } else {
+    float mean, rstd;
+    row_stats(row, P.D, lane, mean, rstd);
+    for (int k = lane * 4; k < P.D; k += 128) {
+      const float4 v = ld4(row + k), h = ld4(sh + k), c = ld4(sc + k);
+      uint2 w;
+      w.x = pack_bf16x2((v.x - mean) * rstd * (1.f + c.x) + h.x, (v.y - mean) * rstd * (1.f + c.y) + h.y);
+      w.y = pack_bf16x2((v.z - mean) * rstd * (1.f + c.z) + h.z, (v.w - mean) * rstd * (1.f + c.w) + h.w);
+      *reinterpret_cast<uint2*>(o + k) = w;
+    }
   }
 }
 
@@ -455,35 +508,44 @@ __global__ void conv3x3_s2_kernel(const float* __restrict__ a, const float* __re
     if (ox0 + p < go) y[((static_cast<long long>(b) * go + oy) * go + ox0 + p) * C + oc] = acc[p];
 }
 
-__global__ void tpm_tail_kernel(const float* __restrict__ y2, int go, int C, const float* __restrict__ fc1_w,
-                                const float* __restrict__ fc1_b, const float* __restrict__ fc2_w, const float* __restrict__ fc2_b,
-                                float eps, float* __restrict__ alpha_beta) {
+// adaptive_avg_pool2d(16,16) -> global max -> fc1 -> SiLU -> fc2 -> exp + eps.  One block of 1024 threads per sample:
+// thread = (cell group 0..7, channel); each group reduces 32 of the 256 pooled cells, then a shared-memory max.
+__global__ void __launch_bounds__(1024) tpm_tail_kernel(const float* __restrict__ y2, int go, int C, const float* __restrict__ fc1_w,
+                                                        const float* __restrict__ fc1_b, const float* __restrict__ fc2_w,
+                                                        const float* __restrict__ fc2_b, float eps, float* __restrict__ alpha_beta) {
+  __shared__ float part[8][128];
   __shared__ float pooled[128];
   __shared__ float hid[128];
-  const int b = blockIdx.x, t = threadIdx.x;
+  const int b = blockIdx.x, t = threadIdx.x & 127, grp = threadIdx.x >> 7;
   const float* p = y2 + static_cast<long long>(b) * go * go * C;
+  float mx = -INFINITY;
   if (t < C) {
-    float mx = -INFINITY;
-    for (int i = 0; i < 16; ++i) {
+    for (int cell = grp * 32; cell < grp * 32 + 32; ++cell) {
+      const int i = cell >> 4, j = cell & 15;
       const int r0 = (i * go) / 16, r1 = ((i + 1) * go + 15) / 16;
-      for (int j = 0; j < 16; ++j) {
-        const int c0 = (j * go) / 16, c1 = ((j + 1) * go + 15) / 16;
-        float s = 0.f;
-        for (int r = r0; r < r1; ++r)
-          for (int c = c0; c < c1; ++c) s += p[(static_cast<long long>(r) * go + c) * C + t];
-        mx = fmaxf(mx, s / static_cast<float>((r1 - r0) * (c1 - c0)));
-      }
+      const int c0 = (j * go) / 16, c1 = ((j + 1) * go + 15) / 16;
+      float s = 0.f;
+      for (int r = r0; r < r1; ++r)
+        for (int c = c0; c < c1; ++c) s += p[(static_cast<long long>(r) * go + c) * C + t];
+      mx = fmaxf(mx, s / static_cast<float>((r1 - r0) * (c1 - c0)));
     }
-    pooled[t] = mx;
+  }
+  part[grp][t] = mx;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float m = part[0][t];
+#pragma unroll
+    for (int g2 = 1; g2 < 8; ++g2) m = fmaxf(m, part[g2][t]);
+    pooled[t] = m;
   }
   __syncthreads();
-  if (t < 128) {
+  if (threadIdx.x < 128) {
     float acc = fc1_b[t];
     for (int c = 0; c < C; ++c) acc = fmaf(fc1_w[t * C + c], pooled[c], acc);
     hid[t] = silu_f(acc);
   }
   __syncthreads();
-  if (t < 2) {
+  if (threadIdx.x < 2) {
     float acc = fc2_b[t];
     for (int j = 0; j < 128; ++j) acc = fmaf(fc2_w[t * 128 + j], hid[j], acc);
     alpha_beta[b * 2 + t] = expf(acc) + eps;
@@ -621,7 +683,13 @@ int k_ln_modulate(const LnSeg* segs, int nseg, int D, cudaStream_t s) {
   P.seg[1] = nseg > 1 ? segs[1] : segs[0];
   P.rows0 = static_cast<long long>(segs[0].rows) * segs[0].batch;
   P.rows_total = P.rows0 + (nseg > 1 ? static_cast<long long>(segs[1].rows) * segs[1].batch : 0);
-  ln_modulate_kernel<<<blocks_for(P.rows_total, 8), 256, 0, s>>>(P);
+  const unsigned grid = blocks_for(P.rows_total, 8);
+  if (D == 1536)
+    ln_modulate_kernel<12><<<grid, 256, 0, s>>>(P);
+  else if (D == 384)
+    ln_modulate_kernel<3><<<grid, 256, 0, s>>>(P);
+  else
+    ln_modulate_kernel<0><<<grid, 256, 0, s>>>(P);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
@@ -708,7 +776,7 @@ int k_conv3x3_s2(const float* a, const float* w, const float* bias, float* y, in
 int k_tpm_tail(const float* y2, int B, int go, int C, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b,
                float eps, float* alpha_beta, cudaStream_t s) {
   TPDM_CHECK(C <= 128, TPDM_ERR_SHAPE, "tpm_tail: conv_out_channels %d > 128", C);
-  tpm_tail_kernel<<<B, 128, 0, s>>>(y2, go, C, fc1_w, fc1_b, fc2_w, fc2_b, eps, alpha_beta);
+  tpm_tail_kernel<<<B, 1024, 0, s>>>(y2, go, C, fc1_w, fc1_b, fc2_w, fc2_b, eps, alpha_beta);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

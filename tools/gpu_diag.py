@@ -123,6 +123,13 @@ if __name__ == "__main__":
         attn_case(1, 1357, 4, 64)
         attn_case(1, 1357, 4, 64, q_rows=1024)
         attn_case(2, 4429, 24, 64, 0, True)
+    if which == "gemm_epi":
+        for epi in (0, 1, 2, 3):
+            gemm_case(2, 4096, 1536, 1536, epi, True)
+        for epi in (0, 3):
+            gemm_case(1, 9472, 1536, 1536, epi, True)   # 74 x 6 = 444 tiles = 3 full waves
+            gemm_case(1, 4736, 1536, 1536, epi, True)   # 222 tiles = 1.5 waves
+            gemm_case(1, 2368 * 8, 1536, 1536, epi, True)   # 6 waves
     if which == "attn_big":
         attn_case(2, 4429, 24, 64)
         attn_case(2, 4429, 24, 64)

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtpdm_b200.so")
+LIB_PATH = os.environ.get("TPDM_B200_LIB", os.path.join(HERE, "libtpdm_b200.so"))
 
 c_float_p = C.POINTER(C.c_float)
 vp = C.c_void_p

@@ -187,26 +187,53 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       const int row_base = tc.mt * BM + q * 32;
       int n_chunks = (G.N - n0 + 31) / 32;
       n_chunks = n_chunks > BN / 32 ? BN / 32 : n_chunks;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       int rows = G.rows_per_batch - row_base;
       rows = rows > 32 ? 32 : rows;
       const bool f32_out = G.epi == EPI_BIAS_F32 || G.epi == EPI_GATE_RESIDUAL;
+      const bool resid = G.epi == EPI_GATE_RESIDUAL;
       // Row-contiguous 16-byte global accesses: a lane owns `vec` consecutive columns (8 bf16 / 4 fp32) of one row, so a
       // warp-wide store covers whole 64 B / 128 B row segments instead of 2 bytes per lane.
       const int vec = f32_out ? 4 : 8;
-      const int groups = 32 / vec;            // column groups per 32-column chunk
-      const int cg = lane % groups;           // this lane's column group
-      const int r_in = lane / groups;         // this lane's row within a pass
-      const int rows_per_pass = 32 / groups;  // 4 (bf16) or 8 (fp32) ... passes = 32 / rows_per_pass
-      const float* gate_row = G.epi == EPI_GATE_RESIDUAL ? G.gate + static_cast<long long>(tc.b) * G.gate_stride : nullptr;
-      for (int c = 0; c < n_chunks; ++c) {
+      const int groups = 32 / vec;   // column groups per 32-column chunk
+      const int cg = lane % groups;  // this lane's column group
+      const int r_in = lane / groups;  // this lane's row within a pass (4 rows per pass for bf16, ... 8 passes of 4 for fp32)
+      const float* gate_row = resid ? G.gate + static_cast<long long>(tc.b) * G.gate_stride : nullptr;
+      const long long tile_o0 = static_cast<long long>(tc.b) * G.out_batch_stride + static_cast<long long>(row_base) * G.ldo + n0;
+
+      // residual mode: the read half of out += gate * (acc + bias) does not depend on the accumulator.  While the MMA
+      // warp is still working on this tile, pull the warp's 32 x BN fp32 block towards L2 and the first chunk into
+      // registers; inside the chunk loop the next chunk's rows are always in flight while the current one is combined.
+      auto load_resv = [&](int c, float4 (&rv)[8]) {
+        const int col = n0 + c * 32 + cg * 4;
+        if (col < G.N) {
+          const float* o = reinterpret_cast<const float*>(G.out) + tile_o0 + c * 32 + cg * 4;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + r_in;
+            rv[it] = r < rows ? *reinterpret_cast<const float4*>(o + static_cast<long long>(r) * G.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      float4 resv_a[8], resv_b[8];
+      if (resid) {
+        if (lane < rows) {
+          const float* o = reinterpret_cast<const float*>(G.out) + tile_o0 + static_cast<long long>(lane) * G.ldo;
+          for (int c = 1; c < n_chunks; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(o + c * 32));
+        }
+        load_resv(0, resv_a);
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+
+      auto process_chunk = [&](int c, const float4 (&resv)[8]) {
         const int col = n0 + c * 32 + cg * vec;
         const bool col_ok = col < G.N && rows > 0;
-        const long long o0 = static_cast<long long>(tc.b) * G.out_batch_stride + static_cast<long long>(row_base) * G.ldo + col;
+        const long long o0 = tile_o0 + c * 32 + cg * vec;
         float bias[8], gate[4];
 #pragma unroll
         for (int e = 0; e < 8; ++e) bias[e] = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) gate[e] = 0.f;
         if (col_ok && G.bias) {
           const float4 b0 = *reinterpret_cast<const float4*>(G.bias + col);
           bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
@@ -215,18 +242,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
             bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
           }
         }
-        // residual mode: the read half of the read-modify-write does not depend on the accumulator -- issue all row loads
-        // before waiting on TMEM so their latency overlaps the MMA tail
-        float4 resv[8];
-        if (G.epi == EPI_GATE_RESIDUAL && col_ok) {
+        if (resid && col_ok) {
           const float4 g4 = *reinterpret_cast<const float4*>(gate_row + col);
           gate[0] = g4.x; gate[1] = g4.y; gate[2] = g4.z; gate[3] = g4.w;
-          const float* o = reinterpret_cast<const float*>(G.out) + o0;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + r_in;
-            resv[it] = r < rows ? *reinterpret_cast<const float4*>(o + static_cast<long long>(r) * G.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
         }
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
@@ -266,7 +284,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
             }
           } else {
             float* o = reinterpret_cast<float*>(G.out) + o0;
-            const bool resid = G.epi == EPI_GATE_RESIDUAL;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               const int r = it * 4 + r_in;
@@ -282,6 +299,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
           }
         }
         __syncwarp();
+      };
+
+      for (int c = 0; c < n_chunks; c += 2) {
+        if (resid && c + 1 < n_chunks) load_resv(c + 1, resv_b);
+        process_chunk(c, resv_a);
+        if (c + 1 < n_chunks) {
+          if (resid && c + 2 < n_chunks) load_resv(c + 2, resv_a);
+          process_chunk(c + 1, resv_b);
+        }
       }
       if (++acc == 2) {
         acc = 0;

@@ -299,3 +299,120 @@ def test_mmdit_forward_sd3_medium_1024_vs_oracle():
     assert rel(h1, rh1) < 1e-3
     assert rel(h2, rh2) < VEL_TOL
     assert rel(v, rv) < VEL_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# other BASELINE.json configs as parity cases (reduced depth keeps the fp32 oracle cheap; widths / sequence lengths are
+# the real ones) and size-independent properties at full size
+# ---------------------------------------------------------------------------------------------------------------
+def _sd3m_pair(num_layers, sample_size, qk_norm=None):
+    from oracle import sd3_oracle as O
+    from tpdm_b200.transformer_sd3 import CustomSD3Transformer2DModel
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.sd3_medium_config(sample_size=sample_size, qk_norm=qk_norm)
+    cfg.num_layers = num_layers
+    torch.manual_seed(4321)
+    ora = O.OracleSD3Transformer(cfg).requires_grad_(False).eval().to("cuda")
+    model = CustomSD3Transformer2DModel(sample_size=sample_size, num_layers=num_layers, attention_head_dim=64, num_attention_heads=24,
+                                        caption_projection_dim=1536, pos_embed_max_size=192, qk_norm=qk_norm, device="cuda",
+                                        dtype=torch.bfloat16)
+    model.load_state_dict(ora.state_dict())
+    ora.load_state_dict(model.state_dict())
+    return ora, model
+
+
+def test_mmdit_2048_long_sequence_vs_oracle():
+    """BASELINE config 5: 16 384 image tokens + 333 text tokens (S = 16 717), batch 1 with CFG (Bt = 2)."""
+    ora, model = _sd3m_pair(num_layers=2, sample_size=256)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    lat = torch.randn(1, 16, 256, 256, device="cuda", generator=g).repeat(2, 1, 1, 1)
+    enc = torch.randn(2, 333, 4096, device="cuda", generator=g)
+    pooled = torch.randn(2, 2048, device="cuda", generator=g)
+    ts = torch.tensor([400.0, 400.0], device="cuda")
+    with torch.no_grad():
+        rv, rt, rh1, rh2 = ora(lat, enc, pooled, ts)
+    v, temb, h1, h2 = model(lat, enc, pooled, ts, return_dict=False)
+    assert v.shape == (2, 16, 256, 256)
+    assert rel(h2, rh2) < VEL_TOL and rel(v, rv) < VEL_TOL
+
+
+def test_mmdit_512_batch32_qknorm_vs_oracle():
+    """BASELINE config 4 shape: 512^2, 16 rollouts with CFG -> transformer batch 32; QK-RMSNorm on."""
+    ora, model = _sd3m_pair(num_layers=2, sample_size=64, qk_norm="rms_norm")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    lat = torch.randn(32, 16, 64, 64, device="cuda", generator=g)
+    enc = torch.randn(32, 333, 4096, device="cuda", generator=g)
+    pooled = torch.randn(32, 2048, device="cuda", generator=g)
+    ts = torch.rand(32, device="cuda", generator=g) * 1000
+    with torch.no_grad():
+        rv, rt, rh1, rh2 = ora(lat, enc, pooled, ts)
+    v, temb, h1, h2 = model(lat, enc, pooled, ts, return_dict=False)
+    assert rel(temb, rt) < 2e-3 and rel(h2, rh2) < VEL_TOL and rel(v, rv) < VEL_TOL
+
+
+def test_attention_full_size_properties(L):
+    """S = 4429, H = 24 (SD3-medium 1024^2): rows of softmax sum to one (V = 1 -> O = 1) and the result does not depend
+    on the order of the keys."""
+    torch.manual_seed(6)
+    lib = L.load()
+    Bt, S, H, d = 1, 4429, 24, 64
+    qkv = torch.randn(Bt, S, 3, H, d, device="cuda").bfloat16()
+    ones = qkv.clone()
+    ones[:, :, 2] = 1.0
+    out = torch.zeros(Bt, S, H, d, device="cuda", dtype=torch.bfloat16)
+    L.check(lib.tpdm_joint_attention(L.ptr(ones), L.ptr(out), Bt, S, H, 64, d, 0, None))
+    torch.cuda.synchronize()
+    assert float((out.float() - 1.0).abs().max()) < 1e-2
+    base = torch.zeros_like(out)
+    L.check(lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(base), Bt, S, H, 64, d, 0, None))
+    perm = torch.randperm(S, device="cuda")
+    shuffled = qkv.clone()
+    shuffled[:, :, 1:] = qkv[:, perm, 1:]          # permute keys and values together, queries stay
+    out2 = torch.zeros_like(out)
+    L.check(lib.tpdm_joint_attention(L.ptr(shuffled.contiguous()), L.ptr(out2), Bt, S, H, 64, d, 0, None))
+    torch.cuda.synchronize()
+    assert rel(out2, base) < 6e-3
+
+
+def test_gemm_linearity_full_size(L):
+    """QKV shape of SD3-medium 1024^2: A (W1 + W2)^T == A W1^T + A W2^T within bf16 rounding of the weights."""
+    torch.manual_seed(7)
+    lib = L.load()
+    A = (torch.randn(2, 4096, 1536, device="cuda") * 0.5).bfloat16()
+    W1 = (torch.randn(4608, 1536, device="cuda") * 0.03).bfloat16()
+    W2 = (torch.randn(4608, 1536, device="cuda") * 0.03).bfloat16()
+    Ws = (W1.float() + W2.float()).bfloat16()
+    outs = []
+    for W in (W1, W2, Ws):
+        o = torch.zeros(2, 4096, 4608, device="cuda")
+        L.check(lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), None, None, L.ptr(o), 2, 4096, 4608, 1536, 1, None))
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert rel(outs[0] + outs[1], outs[2]) < 4e-3
+
+
+def test_sd3_medium_trajectory_is_deterministic_and_terminates():
+    """BASELINE config 1 at full size: the loop stops by itself (sigma_next < min_sigma), one masked step after sigma falls
+    below min_sigma exactly as the reference does, and two runs are bit-identical."""
+    from tpdm_b200.modeling_sd3_pnt import SD3_MEDIUM_TRANSFORMER_CONFIG, SD3PredictNextTimeStepModel
+
+    torch.manual_seed(11)
+    model = SD3PredictNextTimeStepModel(transformer_config=SD3_MEDIUM_TRANSFORMER_CONFIG, torch_dtype=torch.bfloat16, device="cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    kw = dict(prompt_embeds=torch.randn(1, 333, 4096, device="cuda", generator=g),
+              negative_prompt_embeds=torch.randn(1, 333, 4096, device="cuda", generator=g),
+              pooled_prompt_embeds=torch.randn(1, 2048, device="cuda", generator=g),
+              negative_pooled_prompt_embeds=torch.randn(1, 2048, device="cuda", generator=g),
+              latents=torch.randn(1, 16, 128, 128, device="cuda", generator=g))
+    a = model(**kw, max_inference_steps=28, predict=True)
+    b = model(**kw, max_inference_steps=28, predict=True)
+    T = a.sigmas.shape[1]
+    assert 10 < T < 28
+    assert torch.equal(a.sigmas, b.sigmas) and torch.equal(a.latents, b.latents)
+    sig = a.sigmas[0].cpu()
+    assert bool((sig[:-1] > sig[1:]).all()) and float(sig[-1]) < model.min_sigma
+    assert torch.isfinite(a.latents).all() and torch.isfinite(a.logprobs).all()
+    alpha, beta = a.alphas[0, 0].item(), a.betas[0, 0].item()
+    assert abs(float(sig[0]) - (alpha - 1) / (alpha + beta - 2)) < 1e-5     # first step: sigma_1 = 1 * Beta mode

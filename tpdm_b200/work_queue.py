@@ -1,0 +1,73 @@
+"""Prompt sharding for multi-GPU sampling.
+
+Trajectories are independent per prompt and TPDM makes their lengths differ, so a static split leaves GPUs idle.  Ranks
+instead claim prompt indices from one global ticket counter.  The counter lives in the torch.distributed key-value store
+(``store.add`` is an atomic fetch-add served by rank 0's TCPStore), i.e. there is no collective on the data path and a
+rank never waits for another rank.  Works identically under the gloo and nccl backends and without torch.distributed
+(single process)."""
+from __future__ import annotations
+
+from typing import Callable, Dict, Iterator, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+class PromptQueue:
+    def __init__(self, n_prompts: int, name: str = "tpdm_prompt_ticket", store=None):
+        self.n = int(n_prompts)
+        self.key = name
+        self._local = 0
+        self.store = store
+        if store is None and dist.is_available() and dist.is_initialized():
+            self.store = dist.distributed_c10d._get_default_store()
+
+    def claim(self) -> Optional[int]:
+        """Next unclaimed prompt index, or None when the queue is drained."""
+        if self.store is None:
+            idx, self._local = self._local, self._local + 1
+        else:
+            idx = int(self.store.add(self.key, 1)) - 1
+        return idx if idx < self.n else None
+
+    def __iter__(self) -> Iterator[int]:
+        while True:
+            idx = self.claim()
+            if idx is None:
+                return
+            yield idx
+
+
+def static_shard(n_prompts: int, rank: int, world: int) -> List[int]:
+    """Round-robin split (what the bench's weak-scaling run uses: every rank owns prompts rank, rank+world, ...)."""
+    return list(range(rank, n_prompts, world))
+
+
+def sample_prompts(run_one: Callable[[int], Dict], n_prompts: int, dynamic: bool = True, name: str = "tpdm_prompt_ticket") -> Dict[int, Dict]:
+    """Runs ``run_one(prompt_index)`` for this rank's share of ``n_prompts`` and returns {index: result}."""
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    indices = PromptQueue(n_prompts, name) if dynamic else static_shard(n_prompts, rank, world)
+    return {i: run_one(i) for i in indices}
+
+
+def gather_results(local: Dict[int, Dict]) -> Optional[Dict[int, Dict]]:
+    """Bookkeeping only (step counts, timings): gathers the per-rank dicts on rank 0."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return dict(local)
+    out = [None] * dist.get_world_size() if dist.get_rank() == 0 else None
+    dist.gather_object(local, out, dst=0)
+    if dist.get_rank() != 0:
+        return None
+    merged: Dict[int, Dict] = {}
+    for d in out:
+        merged.update(d)
+    return merged
+
+
+def max_over_ranks(value: float, device: Optional[torch.device] = None) -> float:
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -177,6 +177,39 @@ typedef struct tpdm_sample_state {
 } tpdm_sample_state;
 int tpdm_sample_state_get(tpdm_plan* plan, tpdm_sample_state* out);
 
+/* ---- training half: TimePredictor replay with gradients, PPO-clip loss, clip + AdamW ----------------------------------
+ * Replaces only_predict_logprobs (modeling_sd3_pnt.py:670-726), the ratio / PPO-clip loss / backward of
+ * src/train/rloo_trainer.py:485-501 and clip_grad_norm_ + optimizer.step (:505-523) for the TimePredictor (the MMDiT is
+ * frozen).  Parameters live in ONE flat fp32 buffer; tpdm_tpm_param_offsets fills 13 element offsets (last = total):
+ * conv1.weight as [C1][9][2D] (oc, ky*3+kx, c) | conv1.bias | norm1.linear.weight [2C1][D] | norm1.linear.bias |
+ * norm1.norm.weight | norm1.norm.bias | conv2.weight as [9][C1][C1] (tap, c, oc) | conv2.bias | fc1.weight | fc1.bias |
+ * fc2.weight | fc2.bias.  Gradients use the same layout, so the data-parallel exchange is one all-reduce of one buffer. */
+typedef struct tpdm_tpm_trainer tpdm_tpm_trainer;
+int tpdm_tpm_param_offsets(int D, int C1, long long* out13);
+size_t tpdm_tpm_trainer_workspace_bytes(int D, int C1, int g, int max_samples);
+int tpdm_tpm_trainer_create(int D, int C1, int g, int max_samples, float tpm_epsilon, void* workspace, size_t bytes,
+                            tpdm_tpm_trainer** out);
+int tpdm_tpm_trainer_destroy(tpdm_tpm_trainer* t);
+/* params / grads: flat fp32 device buffers (layout above); conv1_w_bf16: bf16 copy of the first C1*9*2D parameters */
+int tpdm_tpm_trainer_bind(tpdm_tpm_trainer* t, float* params, float* grads, void* conv1_w_bf16);
+/* x_nhwc bf16 [ns][g][g][2D] (as recorded by tpdm_sample_state.tpm_input), temb [ns][D] -> alpha_beta [ns][2]; keeps the
+ * activations the backward needs (x_nhwc / temb are borrowed until the backward has run) */
+int tpdm_tpm_train_forward(tpdm_tpm_trainer* t, const void* x_nhwc, const float* temb, int ns, float* alpha_beta,
+                           void* stream);
+/* dz [ns][2] = d loss / d (fc2 output, i.e. log(alpha - eps), log(beta - eps)); OVERWRITES the bound grads buffer */
+int tpdm_tpm_train_backward(tpdm_tpm_trainer* t, const float* dz, void* stream);
+/* alpha_beta [mb*T][2] in (sample, step) order, sigmas / old_logprobs [mb][T] (old_logprobs with 1.0 at masked steps, as
+ * the rollout returns them), advantages [mb] -> new_logprobs [mb][T], dz [mb*T][2],
+ * stats4 = {loss, clip fraction, approx KL, mean ratio} (device) */
+int tpdm_ppo_clip_loss(const float* alpha_beta, const float* sigmas, const float* old_logprobs, const float* advantages,
+                       int mb, int T, float min_sigma, float epsilon, int relative, float cliprange, float tpm_epsilon,
+                       float* new_logprobs, float* dz, float* stats4, void* stream);
+/* g = grads * grad_scale; clip to max_grad_norm (<= 0: off); AdamW (decoupled weight decay); non-finite norm skips the
+ * update; the first bf16_n parameters are mirrored to bf16_copy.  scratch_sumsq: 1 double on the device (holds |g|^2 after). */
+int tpdm_adamw_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, float max_grad_norm, int step, float grad_scale, double* scratch_sumsq,
+                    void* bf16_copy, long long bf16_n, void* stream);
+
 /* ---- measurement hooks used by bench.py -------------------------------------------------------------------------- */
 /* kernels launched by this library in this process since the last reset */
 long long tpdm_launch_count(int reset);
@@ -195,6 +228,9 @@ int tpdm_joint_attention(const void* qkv, void* out, int Bt, int S, int H, int d
 /* conv3x3 pad 1 over NHWC bf16 x [batch][g][g][C], w bf16 [N][9][C] -> out fp32 [batch][g*g][N] */
 int tpdm_conv3x3_nhwc(const void* x, const void* w, const float* bias, float* out, int batch, int g, int C, int N,
                       void* stream);
+/* conv3x3 (pad 1) weight gradient: dyt bf16 [samples][M][g*g], x bf16 three x-shifted NCHW copies [samples][3][C][g][g]
+ * (copy k = X[..., x + k - 1], zero outside) -> dw fp32 [M][9][C] */
+int tpdm_conv3x3_wgrad(const void* dyt, const void* x_shifted_nchw, float* dw, int samples, int g, int C, int M, void* stream);
 /* LayerNorm(eps 1e-6, no affine) * (1 + scale[b]) + shift[b] : x fp32 [batch][rows][D] -> bf16 */
 int tpdm_ln_modulate(const float* x, const float* shift, const float* scale, int mod_stride, void* out_bf16, int batch,
                      int rows, int D, void* stream);

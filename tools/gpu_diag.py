@@ -130,6 +130,23 @@ if __name__ == "__main__":
             gemm_case(1, 9472, 1536, 1536, epi, True)   # 74 x 6 = 444 tiles = 3 full waves
             gemm_case(1, 4736, 1536, 1536, epi, True)   # 222 tiles = 1.5 waves
             gemm_case(1, 2368 * 8, 1536, 1536, epi, True)   # 6 waves
+    if which == "wgrad":
+        cases = ((1, 16, 256),) if len(sys.argv) > 2 else ((1, 16, 256), (3, 16, 256), (2, 32, 512), (1, 64, 3072))
+        for (ns, g, Cc) in cases:
+            M = 128
+            x = torch.randn(ns, Cc, g, g, device=dev).bfloat16()
+            dy = torch.randn(ns, M, g, g, device=dev).bfloat16()
+            xs = torch.zeros(ns, 3, Cc, g, g, device=dev, dtype=torch.bfloat16)
+            xs[:, 1] = x
+            xs[:, 0, :, :, 1:] = x[:, :, :, :-1]
+            xs[:, 2, :, :, :-1] = x[:, :, :, 1:]
+            w = torch.zeros(M, Cc, 3, 3, device=dev, requires_grad=True)
+            torch.nn.functional.conv2d(x.float(), w, padding=1).backward(dy.float())
+            ref = w.grad.permute(0, 2, 3, 1).reshape(M, 9 * Cc)
+            out = torch.full((M, 9 * Cc), 7.0, device=dev)
+            st = lib.tpdm_conv3x3_wgrad(L.ptr(dy.reshape(ns, M, g * g).contiguous()), L.ptr(xs), L.ptr(out), ns, g, Cc, M, None)
+            torch.cuda.synchronize()
+            print(f"wgrad ns={ns} g={g} C={Cc}: status={st} rel={rel(out, ref):.3e}", flush=True)
     if which == "attn_big":
         attn_case(2, 4429, 24, 64)
         attn_case(2, 4429, 24, 64)

@@ -59,12 +59,23 @@ EXPORTS = {
     "tpdm_sample_begin": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, vp, C.c_ulonglong, vp]),
     "tpdm_sample_step": (C.c_int, [vp, C.c_int, vp]),
     "tpdm_sample_state_get": (C.c_int, [vp, C.POINTER(TpdmSampleState)]),
+    "tpdm_tpm_param_offsets": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
+    "tpdm_tpm_trainer_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "tpdm_tpm_trainer_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, C.c_size_t, C.POINTER(vp)]),
+    "tpdm_tpm_trainer_destroy": (C.c_int, [vp]),
+    "tpdm_tpm_trainer_bind": (C.c_int, [vp, vp, vp, vp]),
+    "tpdm_tpm_train_forward": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
+    "tpdm_tpm_train_backward": (C.c_int, [vp, vp, vp]),
+    "tpdm_ppo_clip_loss": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]),
+    "tpdm_adamw_step": (C.c_int, [vp, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
+                                  C.c_float, vp, vp, C.c_longlong, vp]),
     "tpdm_launch_count": (C.c_longlong, [C.c_int]),
     "tpdm_profile_start": (C.c_int, [C.c_int]),
     "tpdm_profile_stop": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "tpdm_gemm_bf16": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tpdm_joint_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tpdm_conv3x3_nhwc": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
+    "tpdm_conv3x3_wgrad": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tpdm_ln_modulate": (C.c_int, [vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp]),
 }
 

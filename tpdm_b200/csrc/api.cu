@@ -515,6 +515,13 @@ int tpdm_conv3x3_nhwc(const void* x, const void* w, const float* bias, float* ou
   return gemm_launch(&op, 1, static_cast<cudaStream_t>(stream));
 }
 
+int tpdm_conv3x3_wgrad(const void* dyt, const void* x_shifted_nchw, float* dw, int samples, int g, int C, int M, void* stream) {
+  TPDM_CHECK(dyt && x_shifted_nchw && dw, TPDM_ERR_ARG, "tpdm_conv3x3_wgrad: null argument");
+  GemmOp op;
+  TPDM_TRY(gemm_op_init_conv3x3_wgrad(&op, dyt, x_shifted_nchw, samples, g, C, M, dw));
+  return gemm_launch(&op, 1, static_cast<cudaStream_t>(stream));
+}
+
 int tpdm_ln_modulate(const float* x, const float* shift, const float* scale, int mod_stride, void* out_bf16, int batch, int rows, int D,
                      void* stream) {
   TPDM_CHECK(x && shift && scale && out_bf16, TPDM_ERR_ARG, "tpdm_ln_modulate: null argument");

@@ -119,6 +119,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
           uint8_t* sA = smem + stage * L::kStageBytes;
           uint8_t* sB = sA + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (G.conv == 2) {
+            // conv1 weight gradient: K runs over (sample, 64-pixel block); A = dY^T [sample][oc][pix],
+            // B = X (NCHW) shifted by the tile's tap: 64 consecutive pixels of `BN` channels per k-block
+            const int sample = kb / G.kb_per_tap, pblk = kb - sample * G.kb_per_tap;
+            const int tap = tc.nt / G.wg_ctiles, c0 = (tc.nt - tap * G.wg_ctiles) * BN;
+            tma_load_3d(sA, &G.tmA, &full_bar[stage], pblk * BK, 0, sample);
+            // B: pixels (y, x) are one flattened, contiguous dimension, so a 64-pixel block is always a 128-byte inner
+            // box; the row shift (ky) is +-g pixels with zero fill past either end, the column shift (kx) selects one of
+            // three pre-shifted copies so the innermost (swizzled) coordinate stays 16-byte aligned
+            tma_load_4d(sB, &G.tmB, &full_bar[stage], pblk * BK + (tap / 3 - 1) * G.wg_px, c0, tap % 3, sample);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           if (G.conv) {
             const int tap = kb / G.kb_per_tap;
             const int c0 = (kb - tap * G.kb_per_tap) * BK;
@@ -402,6 +418,37 @@ int gemm_op_init_conv3x3(GemmOp* op, const void* X, int batch, int g, int C, con
   uint32_t box[4] = {BK, static_cast<uint32_t>(g), static_cast<uint32_t>(BM / g), 1};
   TPDM_TRY(encode_tmap_bf16(&op->tmA, X, 4, dims, strides, box));
   return finish_op(op, W, N, 9 * C, epi, out, static_cast<long long>(g) * g * ldo, ldo, bias, nullptr, 0);
+}
+
+int gemm_op_init_conv3x3_wgrad(GemmOp* op, const void* dYt, const void* Xnchw, int samples, int g, int C, int M, float* dW) {
+  *op = GemmOp{};
+  TPDM_CHECK(g >= 8 && g <= 128 && (g & (g - 1)) == 0, TPDM_ERR_SHAPE, "conv3x3 wgrad: grid side %d must be a power of two in [8,128]", g);
+  TPDM_CHECK(C % 256 == 0 && M <= BM && M % 8 == 0, TPDM_ERR_SHAPE, "conv3x3 wgrad: C=%d must be a multiple of 256 and M=%d <= 128", C, M);
+  const int P = g * g;
+  op->rows_per_batch = M;
+  op->batch = 1;
+  op->tiles_m_per_batch = 1;
+  op->conv = 2;
+  op->wg_px = g;                  // pixels per image row (= the flattened shift of one row)
+  op->wg_ctiles = C / 256;
+  op->kb_per_tap = P / BK;        // k-blocks per sample
+  op->N = 9 * C;
+  op->K = samples * P;
+  op->block_n = 256;
+  op->tiles_n = 9 * (C / 256);
+  op->num_tiles = op->tiles_n;
+  op->epi = EPI_BIAS_F32;
+  op->out = dW;
+  op->out_batch_stride = 0;
+  op->ldo = 9 * C;
+  uint64_t adims[3] = {static_cast<uint64_t>(P), static_cast<uint64_t>(M), static_cast<uint64_t>(samples)};
+  uint64_t astr[2] = {static_cast<uint64_t>(P) * 2, static_cast<uint64_t>(P) * M * 2};
+  uint32_t abox[3] = {BK, BM, 1};
+  TPDM_TRY(encode_tmap_bf16(&op->tmA, dYt, 3, adims, astr, abox));
+  uint64_t bdims[4] = {static_cast<uint64_t>(P), static_cast<uint64_t>(C), 3, static_cast<uint64_t>(samples)};
+  uint64_t bstr[3] = {static_cast<uint64_t>(P) * 2, static_cast<uint64_t>(P) * C * 2, static_cast<uint64_t>(P) * C * 3 * 2};
+  uint32_t bbox[4] = {BK, 256, 1, 1};
+  return encode_tmap_bf16(&op->tmB, Xnchw, 4, bdims, bstr, bbox);
 }
 
 int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {

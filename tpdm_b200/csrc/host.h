@@ -64,7 +64,8 @@ struct alignas(64) GemmOp {
   CUtensorMap tmB;  // (K, N) box (64, BN)
   int rows_per_batch, batch, N, K;
   int tiles_m_per_batch, tiles_n, num_tiles, block_n;
-  int conv, conv_by, kb_per_tap, epi;
+  int conv, conv_by, kb_per_tap, epi;  // conv: 0 plain, 1 conv3x3 forward, 2 conv3x3 weight gradient
+  int wg_px, wg_bpr, wg_ctiles, wg_pad;
   void* out;
   long long out_batch_stride;  // elements between batches of the output
   int ldo;                     // output leading dimension (elements)
@@ -80,6 +81,10 @@ int gemm_op_init(GemmOp* op, const void* A, long long a_row_stride, long long a_
 // implicit-GEMM 3x3 / pad 1 / stride 1 convolution over NHWC bf16 X[b][g][g][C]; W packed [N][9*C] (tap-major, tap=ky*3+kx).
 int gemm_op_init_conv3x3(GemmOp* op, const void* X, int batch, int g, int C, const void* W, int N, int epi, void* out,
                          int ldo, const float* bias);
+// conv3x3 (pad 1, stride 1) weight gradient as a GEMM: dW[m][tap][c] = sum_{sample,pix} dYt[sample][m][pix] * X[sample][c][pix+tap]
+// dYt bf16 [samples][M][g*g]; X bf16 as THREE x-shifted NCHW copies [samples][3][C][g][g], copy k holding X[.., x + k - 1]
+// (zero outside), so no TMA load needs an unaligned innermost coordinate; dW fp32 [M][9][C] (overwritten)
+int gemm_op_init_conv3x3_wgrad(GemmOp* op, const void* dYt, const void* Xnchw, int samples, int g, int C, int M, float* dW);
 // one persistent launch over up to two ops (e.g. image stream + text stream)
 int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream);
 

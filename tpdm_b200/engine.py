@@ -35,11 +35,17 @@ class PackedWeights:
 
     def __init__(self):
         self.keep = []           # owning references
+        self.by_name = {}
         self.struct = L.TpdmWeights()
         self.blocks = None
 
     def _set(self, struct, name, tensor):
+        if struct is self.struct and name in self.by_name:   # refresh: same storage, same pointers (plans stay valid)
+            self.by_name[name].copy_(tensor)
+            return
         self.keep.append(tensor)
+        if struct is self.struct:
+            self.by_name[name] = tensor
         setattr(struct, name, tensor.data_ptr())
 
 
@@ -229,6 +235,13 @@ class Engine:
                 L.load().tpdm_destroy(self.ctx)
         except Exception:
             pass
+
+    def refresh_time_predictor(self, tpm_sd: Dict[str, torch.Tensor]) -> None:
+        """Copy new TimePredictor values into the already packed device tensors (pointers and TMA descriptors unchanged)."""
+        if not self.has_tpm:
+            raise RuntimeError("engine was built without a TimePredictor")
+        with torch.cuda.device(self.device):
+            pack_time_predictor(self.weights, tpm_sd, self.device)
 
     def plan(self, batch: int, cfg_pairs: bool, latent: int, n_text: int, max_steps: int = 1) -> Plan:
         key = (batch, bool(cfg_pairs), latent, n_text, max_steps)

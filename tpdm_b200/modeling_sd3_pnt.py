@@ -166,14 +166,18 @@ class SD3PredictNextTimeStepModel(nn.Module):
         return self.transformer.dtype
 
     def get_engine(self) -> Engine:
-        key = (self.transformer._weights_key(), self.time_predictor._weights_key(), self.min_sigma, self.relative, self.prediction_type)
-        if self._engine is None or key != self._engine_key:
+        key_t = (self.transformer._weights_key(), self.min_sigma, self.relative, self.prediction_type)
+        key_p = self.time_predictor._weights_key()
+        if self._engine is None or key_t != self._engine_key[0]:
             self._engine = Engine(self.transformer.engine_config(), self.device, transformer_sd=self.transformer.state_dict(),
                                   transformer_cfg=self.transformer.config, tpm_sd=self.time_predictor.state_dict(),
                                   min_sigma=self.min_sigma, relative=self.relative, prediction_type=self.prediction_type,
                                   epsilon=self.epsilon, tpm_epsilon=self.time_predictor.epsilon,
                                   tpm_channels=self.time_predictor.conv_out_channels)
-            self._engine_key = key
+        elif key_p != self._engine_key[1]:
+            # only the TimePredictor changed (an optimizer step): refresh its packed tensors in place, keep the 4 GB MMDiT pack
+            self._engine.refresh_time_predictor(self.time_predictor.state_dict())
+        self._engine_key = (key_t, key_p)
         return self._engine
 
     def encode_prompt(self, *args, **kwargs):
@@ -185,7 +189,12 @@ class SD3PredictNextTimeStepModel(nn.Module):
         if latents is not None:
             return latents.to(device=device, dtype=dtype)
         shape = (batch_size, num_channels_latents, int(height) // self.vae_scale_factor, int(width) // self.vae_scale_factor)
-        return torch.randn(shape, generator=generator, device=device, dtype=dtype)
+        # diffusers.utils.torch_utils.randn_tensor semantics: a CPU generator draws on the CPU, then the tensor is moved
+        gen = generator[0] if isinstance(generator, (list, tuple)) else generator
+        gen_device = gen.device if gen is not None else torch.device(device)
+        if gen_device.type != torch.device(device).type:
+            return torch.randn(shape, generator=gen, device=gen_device, dtype=dtype).to(device)
+        return torch.randn(shape, generator=gen, device=device, dtype=dtype)
 
     @torch.no_grad()
     def forward(

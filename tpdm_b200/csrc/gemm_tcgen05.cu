@@ -41,7 +41,7 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRing = kStages * kStageBytes;
-  static constexpr int kEpi = 4 * 32 * kStagePad * 4;
+  static constexpr int kEpi = 4 * 32 * kStagePad * 4 + 4 * 2 * BN * 4;  // transpose staging + per-warp bias / gate vectors of the tile
   static constexpr int kBarOff = kRing + kEpi;
   static constexpr int kTotal = kBarOff + 256 + 1024;  // + barriers + alignment slack
 };
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     float* st = epi_stage + (warp - 2) * 32 * kStagePad;
+    float* sbias = epi_stage + 4 * 32 * kStagePad + (warp - 2) * 2 * BN;  // [0,BN) bias, [BN,2BN) gate of the current tile
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -232,6 +233,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
           }
         }
       };
+      // bias / gate of the tile's columns: fetched once per tile into shared memory while the MMA is still running (loading
+      // them per 32-column chunk put an L2 round trip on the critical path of every chunk)
+      for (int k = lane * 4; k < BN; k += 128) {
+        const int col = n0 + k;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = b4;
+        if (col < G.N) {
+          if (G.bias) b4 = *reinterpret_cast<const float4*>(G.bias + col);
+          if (resid) g4 = *reinterpret_cast<const float4*>(gate_row + col);
+        }
+        *reinterpret_cast<float4*>(sbias + k) = b4;
+        *reinterpret_cast<float4*>(sbias + BN + k) = g4;
+      }
+      __syncwarp();
       float4 resv_a[8], resv_b[8];
       if (resid) {
         if (lane < rows) {
@@ -248,20 +262,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
         const bool col_ok = col < G.N && rows > 0;
         const long long o0 = tile_o0 + c * 32 + cg * vec;
         float bias[8], gate[4];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) bias[e] = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) gate[e] = 0.f;
-        if (col_ok && G.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(G.bias + col);
+        {
+          const float* sb = sbias + c * 32 + cg * vec;
+          const float4 b0 = *reinterpret_cast<const float4*>(sb);
           bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
           if (!f32_out) {
-            const float4 b1 = *reinterpret_cast<const float4*>(G.bias + col + 4);
+            const float4 b1 = *reinterpret_cast<const float4*>(sb + 4);
             bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+          } else {
+            bias[4] = bias[5] = bias[6] = bias[7] = 0.f;
           }
-        }
-        if (resid && col_ok) {
-          const float4 g4 = *reinterpret_cast<const float4*>(gate_row + col);
+          const float4 g4 = *reinterpret_cast<const float4*>(sb + BN);
           gate[0] = g4.x; gate[1] = g4.y; gate[2] = g4.z; gate[3] = g4.w;
         }
         uint32_t v[32];

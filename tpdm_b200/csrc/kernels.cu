@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   }
   __syncthreads();
   const int top = (pos_max - gh) / 2, left = (pos_max - gw) / 2;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+  for (int d = blockIdx.z * blockDim.x + threadIdx.x; d < D; d += gridDim.z * blockDim.x) {
     float w[64];
     const float* wr = Wp + static_cast<long long>(d) * KK;
 #pragma unroll
@@ -235,60 +235,81 @@ __device__ __forceinline__ void row_stats(const float* __restrict__ row, int D, 
 struct LnParams {
   LnSeg seg[2];
   int nseg, D;
-  long long rows0, rows_total;
+  long long blocks0, blocks_total;  // blocks of segment 0 / of both segments
   const int* skip;
 };
 
-// VPL = float4 per lane (D = 128 * VPL): the row is read from global memory ONCE and kept in registers; VPL = 0 is the
-// generic three-pass route (statistics re-read through L1).
+// One block = 32 consecutive token rows of ONE batch entry of one stream: the batch entry's shift / scale vectors are
+// staged in shared memory once per block, each warp then streams 4 rows (row kept in registers when D = 128 * VPL, read
+// once with no-allocate loads; VPL = 0 is the generic route that re-reads the row through L1 for the statistics).
+constexpr int kLnRowsPerBlock = 32;
+
+__device__ __forceinline__ float4 ld4_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
 template <int VPL>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant__ LnParams P) {
   if (P.skip != nullptr && *P.skip != 0) return;
-  const int lane = threadIdx.x & 31;
-  const long long r = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  if (r >= P.rows_total) return;
-  const int si = r >= P.rows0 ? 1 : 0;
+  extern __shared__ float ln_mod[];  // [D] shift, [D] scale
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int si = static_cast<long long>(blockIdx.x) >= P.blocks0 ? 1 : 0;
   const LnSeg& S = P.seg[si];
-  const long long lr = r - (si ? P.rows0 : 0);
-  const int b = static_cast<int>(lr / S.rows);
-  const float* row = S.x + lr * P.D;
+  const int blk = blockIdx.x - (si ? static_cast<int>(P.blocks0) : 0);
+  const int rb_per_batch = (S.rows + kLnRowsPerBlock - 1) / kLnRowsPerBlock;
+  const int b = blk / rb_per_batch, r0 = (blk - b * rb_per_batch) * kLnRowsPerBlock;
   const float* sh = S.shift + static_cast<long long>(b) * S.mod_stride;
   const float* sc = S.scale + static_cast<long long>(b) * S.mod_stride;
-  bf16* o = S.out + lr * P.D;
-  if constexpr (VPL > 0) {
-    float4 v[VPL];
-    float s = 0.f;
+  for (int k = threadIdx.x * 4; k < P.D; k += 256 * 4) {
+    *reinterpret_cast<float4*>(ln_mod + k) = ld4(sh + k);
+    float4 c = ld4(sc + k);
+    c.x += 1.f; c.y += 1.f; c.z += 1.f; c.w += 1.f;
+    *reinterpret_cast<float4*>(ln_mod + P.D + k) = c;
+  }
+  __syncthreads();
+  for (int rr = warp; rr < kLnRowsPerBlock; rr += 8) {
+    const int r = r0 + rr;
+    if (r >= S.rows) break;
+    const long long lr = static_cast<long long>(b) * S.rows + r;
+    const float* row = S.x + lr * P.D;
+    bf16* o = S.out + lr * P.D;
+    if constexpr (VPL > 0) {
+      float4 v[VPL];
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      v[i] = ld4(row + (i * 32 + lane) * 4);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    const float mean = warp_sum(s) / P.D;
-    float ss = 0.f;
+      for (int i = 0; i < VPL; ++i) {
+        v[i] = ld4_stream(row + (i * 32 + lane) * 4);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+      const float mean = warp_sum(s) / P.D;
+      float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      ss += (a * a + bq * bq) + (c * c + d * d);
-    }
-    const float rstd = rsqrtf(warp_sum(ss) / P.D + 1e-6f);
+      for (int i = 0; i < VPL; ++i) {
+        const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        ss += (a * a + bq * bq) + (c * c + d * d);
+      }
+      const float rstd = rsqrtf(warp_sum(ss) / P.D + 1e-6f);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      const int k = (i * 32 + lane) * 4;
-      const float4 h = ld4(sh + k), c = ld4(sc + k);
-      uint2 w;
-      w.x = pack_bf16x2((v[i].x - mean) * rstd * (1.f + c.x) + h.x, (v[i].y - mean) * rstd * (1.f + c.y) + h.y);
-      w.y = pack_bf16x2((v[i].z - mean) * rstd * (1.f + c.z) + h.z, (v[i].w - mean) * rstd * (1.f + c.w) + h.w);
-      *reinterpret_cast<uint2*>(o + k) = w;
-    }
-  } else {
-    float mean, rstd;
-    row_stats(row, P.D, lane, mean, rstd);
-    for (int k = lane * 4; k < P.D; k += 128) {
-      const float4 v = ld4(row + k), h = ld4(sh + k), c = ld4(sc + k);
-      uint2 w;
-      w.x = pack_bf16x2((v.x - mean) * rstd * (1.f + c.x) + h.x, (v.y - mean) * rstd * (1.f + c.y) + h.y);
-      w.y = pack_bf16x2((v.z - mean) * rstd * (1.f + c.z) + h.z, (v.w - mean) * rstd * (1.f + c.w) + h.w);
-      *reinterpret_cast<uint2*>(o + k) = w;
+      for (int i = 0; i < VPL; ++i) {
+        const int k = (i * 32 + lane) * 4;
+        const float4 h = *reinterpret_cast<const float4*>(ln_mod + k), c = *reinterpret_cast<const float4*>(ln_mod + P.D + k);
+        uint2 w;
+        w.x = pack_bf16x2((v[i].x - mean) * rstd * c.x + h.x, (v[i].y - mean) * rstd * c.y + h.y);
+        w.y = pack_bf16x2((v[i].z - mean) * rstd * c.z + h.z, (v[i].w - mean) * rstd * c.w + h.w);
+        *reinterpret_cast<uint2*>(o + k) = w;
+      }
+    } else {
+      float mean, rstd;
+      row_stats(row, P.D, lane, mean, rstd);
+      for (int k = lane * 4; k < P.D; k += 128) {
+        const float4 v = ld4(row + k), h = *reinterpret_cast<const float4*>(ln_mod + k), c = *reinterpret_cast<const float4*>(ln_mod + P.D + k);
+        uint2 w;
+        w.x = pack_bf16x2((v.x - mean) * rstd * c.x + h.x, (v.y - mean) * rstd * c.y + h.y);
+        w.y = pack_bf16x2((v.z - mean) * rstd * c.z + h.z, (v.w - mean) * rstd * c.w + h.w);
+        *reinterpret_cast<uint2*>(o + k) = w;
+      }
     }
   }
 }
@@ -497,10 +518,14 @@ __global__ void conv3x3_s2_kernel(const float* __restrict__ a, const float* __re
     const int ky = tap / 3, kx = tap % 3;
     const float* wp = w + static_cast<long long>(tap) * C * C + oc;
     const float* ip = in_s + (ky * cols + kx) * C;
-    for (int c = 0; c < C; ++c) {
-      const float wv = wp[static_cast<long long>(c) * C];
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float wv[8];
 #pragma unroll
-      for (int p = 0; p < kC2Pix; ++p) acc[p] = fmaf(wv, ip[2 * p * C + c], acc[p]);
+      for (int u = 0; u < 8; ++u) wv[u] = wp[static_cast<long long>(c0 + u) * C];  // 8 independent (coalesced over oc) loads in flight
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int p = 0; p < kC2Pix; ++p) acc[p] = fmaf(wv[u], ip[2 * p * C + c0 + u], acc[p]);
     }
   }
 #pragma unroll
@@ -520,7 +545,8 @@ __global__ void __launch_bounds__(1024) tpm_tail_kernel(const float* __restrict_
   const float* p = y2 + static_cast<long long>(b) * go * go * C;
   float mx = -INFINITY;
   if (t < C) {
-    for (int cell = grp * 32; cell < grp * 32 + 32; ++cell) {
+#pragma unroll 4
+    for (int cell = grp * 32; cell < grp * 32 + 32; ++cell) {  // unrolled: the cells' loads are independent and stay in flight together
       const int i = cell >> 4, j = cell & 15;
       const int r0 = (i * go) / 16, r1 = ((i + 1) * go + 15) / 16;
       const int c0 = (j * go) / 16, c1 = ((j + 1) * go + 15) / 16;
@@ -541,7 +567,12 @@ __global__ void __launch_bounds__(1024) tpm_tail_kernel(const float* __restrict_
   __syncthreads();
   if (threadIdx.x < 128) {
     float acc = fc1_b[t];
-    for (int c = 0; c < C; ++c) acc = fmaf(fc1_w[t * C + c], pooled[c], acc);
+    const float4* wr = reinterpret_cast<const float4*>(fc1_w + t * C);
+#pragma unroll 8
+    for (int c = 0; c < C / 4; ++c) {
+      const float4 w4 = wr[c];
+      acc = fmaf(w4.x, pooled[4 * c], fmaf(w4.y, pooled[4 * c + 1], fmaf(w4.z, pooled[4 * c + 2], fmaf(w4.w, pooled[4 * c + 3], acc))));
+    }
     hid[t] = silu_f(acc);
   }
   __syncthreads();
@@ -665,7 +696,7 @@ int k_patchify(const float* latents, const float* Wp, const float* bias, const f
   TPDM_CHECK(N % kPatchTok == 0, TPDM_ERR_SHAPE, "patchify: token count %d must be a multiple of %d", N, kPatchTok);
   TPDM_CHECK(Hl / 2 <= pos_max && Wl / 2 <= pos_max, TPDM_ERR_SHAPE, "patchify: grid %dx%d exceeds pos_embed_max_size %d", Hl / 2,
              Wl / 2, pos_max);
-  dim3 grid(N / kPatchTok, Bl);
+  dim3 grid(N / kPatchTok, Bl, (D + 255) / 256);  // one output channel per thread: (N/32) x Bl x D/256 blocks
   patchify_kernel<<<grid, 256, kPatchTok * 64 * sizeof(float), s>>>(latents, Wp, bias, pos_table, pos_max, x, Bl, dup, C, Hl, Wl, D,
                                                                    h1_out, tpm_x);
   count_launch();
@@ -681,15 +712,18 @@ int k_ln_modulate(const LnSeg* segs, int nseg, int D, cudaStream_t s) {
   P.skip = skip_flag();
   P.seg[0] = segs[0];
   P.seg[1] = nseg > 1 ? segs[1] : segs[0];
-  P.rows0 = static_cast<long long>(segs[0].rows) * segs[0].batch;
-  P.rows_total = P.rows0 + (nseg > 1 ? static_cast<long long>(segs[1].rows) * segs[1].batch : 0);
-  const unsigned grid = blocks_for(P.rows_total, 8);
+  auto blocks_of = [](const LnSeg& g) { return static_cast<long long>(g.batch) * ((g.rows + kLnRowsPerBlock - 1) / kLnRowsPerBlock); };
+  P.blocks0 = blocks_of(segs[0]);
+  P.blocks_total = P.blocks0 + (nseg > 1 ? blocks_of(segs[1]) : 0);
+  const unsigned grid = static_cast<unsigned>(P.blocks_total);
+  const size_t smem = static_cast<size_t>(2) * D * sizeof(float);
+  TPDM_CHECK(smem <= 48 * 1024, TPDM_ERR_SHAPE, "ln_modulate: D=%d too large", D);
   if (D == 1536)
-    ln_modulate_kernel<12><<<grid, 256, 0, s>>>(P);
+    ln_modulate_kernel<12><<<grid, 256, smem, s>>>(P);
   else if (D == 384)
-    ln_modulate_kernel<3><<<grid, 256, 0, s>>>(P);
+    ln_modulate_kernel<3><<<grid, 256, smem, s>>>(P);
   else
-    ln_modulate_kernel<0><<<grid, 256, 0, s>>>(P);
+    ln_modulate_kernel<0><<<grid, 256, smem, s>>>(P);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
@@ -763,7 +797,7 @@ int k_gn_mod_silu(const float* y, const double* stats, const float* gn_w, const 
 }
 
 int k_conv3x3_s2(const float* a, const float* w, const float* bias, float* y, int B, int g, int C, cudaStream_t s) {
-  TPDM_CHECK(C <= 1024 && g % 2 == 0, TPDM_ERR_SHAPE, "conv3x3_s2: unsupported shape");
+  TPDM_CHECK(C <= 1024 && C % 8 == 0 && g % 2 == 0, TPDM_ERR_SHAPE, "conv3x3_s2: unsupported shape");
   const int go = g / 2;
   dim3 grid((go + kC2Pix - 1) / kC2Pix, go, B);
   const size_t smem = static_cast<size_t>(3) * (2 * kC2Pix + 1) * C * sizeof(float);

@@ -14,8 +14,10 @@
 //              row-contiguous, then bias / GELU-tanh / gate*x + fp32 residual
 // Up to two independent problems (image stream + text stream) share one launch so the small text GEMM fills the tail wave.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "host.h"
 
 namespace tpdm {
@@ -27,7 +29,6 @@ constexpr int BK = 64;
 constexpr int kStages = 4;
 constexpr int kGemmThreads = 192;
 constexpr int kABytes = BM * BK * 2;
-constexpr int kStagePad = 36;  // floats per staged row: 16-byte aligned rows, conflict-free 128-bit access
 
 struct GemmParams {
   GemmOp op[2];
@@ -204,140 +205,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       const GemmOp& G = P.op[tc.g];
       const int n0 = tc.nt * BN;
       const int row_base = tc.mt * BM + q * 32;
-      int n_chunks = (G.N - n0 + 31) / 32;
-      n_chunks = n_chunks > BN / 32 ? BN / 32 : n_chunks;
-      int rows = G.rows_per_batch - row_base;
-      rows = rows > 32 ? 32 : rows;
-      const bool f32_out = G.epi == EPI_BIAS_F32 || G.epi == EPI_GATE_RESIDUAL;
-      const bool resid = G.epi == EPI_GATE_RESIDUAL;
-      // Row-contiguous 16-byte global accesses: a lane owns `vec` consecutive columns (8 bf16 / 4 fp32) of one row, so a
-      // warp-wide store covers whole 64 B / 128 B row segments instead of 2 bytes per lane.
-      const int vec = f32_out ? 4 : 8;
-      const int groups = 32 / vec;   // column groups per 32-column chunk
-      const int cg = lane % groups;  // this lane's column group
-      const int r_in = lane / groups;  // this lane's row within a pass (4 rows per pass for bf16, ... 8 passes of 4 for fp32)
-      const float* gate_row = resid ? G.gate + static_cast<long long>(tc.b) * G.gate_stride : nullptr;
-      const long long tile_o0 = static_cast<long long>(tc.b) * G.out_batch_stride + static_cast<long long>(row_base) * G.ldo + n0;
-
-      // residual mode: the read half of out += gate * (acc + bias) does not depend on the accumulator.  While the MMA
-      // warp is still working on this tile, pull the warp's 32 x BN fp32 block towards L2 and the first chunk into
-      // registers; inside the chunk loop the next chunk's rows are always in flight while the current one is combined.
-      auto load_resv = [&](int c, float4 (&rv)[8]) {
-        const int col = n0 + c * 32 + cg * 4;
-        if (col < G.N) {
-          const float* o = reinterpret_cast<const float*>(G.out) + tile_o0 + c * 32 + cg * 4;
-#pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + r_in;
-            rv[it] = r < rows ? *reinterpret_cast<const float4*>(o + static_cast<long long>(r) * G.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      };
-      // bias / gate of the tile's columns: fetched once per tile into shared memory while the MMA is still running (loading
-      // them per 32-column chunk put an L2 round trip on the critical path of every chunk)
-      for (int k = lane * 4; k < BN; k += 128) {
-        const int col = n0 + k;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = b4;
-        if (col < G.N) {
-          if (G.bias) b4 = *reinterpret_cast<const float4*>(G.bias + col);
-          if (resid) g4 = *reinterpret_cast<const float4*>(gate_row + col);
-        }
-        *reinterpret_cast<float4*>(sbias + k) = b4;
-        *reinterpret_cast<float4*>(sbias + BN + k) = g4;
-      }
-      __syncwarp();
-      float4 resv_a[8], resv_b[8];
-      if (resid) {
-        if (lane < rows) {
-          const float* o = reinterpret_cast<const float*>(G.out) + tile_o0 + static_cast<long long>(lane) * G.ldo;
-          for (int c = 1; c < n_chunks; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(o + c * 32));
-        }
-        load_resv(0, resv_a);
-      }
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-
-      auto process_chunk = [&](int c, const float4 (&resv)[8]) {
-        const int col = n0 + c * 32 + cg * vec;
-        const bool col_ok = col < G.N && rows > 0;
-        const long long o0 = tile_o0 + c * 32 + cg * vec;
-        float bias[8], gate[4];
-        {
-          const float* sb = sbias + c * 32 + cg * vec;
-          const float4 b0 = *reinterpret_cast<const float4*>(sb);
-          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
-          if (!f32_out) {
-            const float4 b1 = *reinterpret_cast<const float4*>(sb + 4);
-            bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
-          } else {
-            bias[4] = bias[5] = bias[6] = bias[7] = 0.f;
-          }
-          const float4 g4 = *reinterpret_cast<const float4*>(sb + BN);
-          gate[0] = g4.x; gate[1] = g4.y; gate[2] = g4.z; gate[3] = g4.w;
-        }
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
-        tmem_wait_ld();
-        if (c == n_chunks - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(st + lane * kStagePad + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        __syncwarp();
-        if (col_ok) {
-          if (!f32_out) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + o0;
-            const bool gelu = G.epi == EPI_BIAS_GELU_BF16;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int r = it * 8 + r_in;
-              if (r < rows) {
-                const float4 x0 = *reinterpret_cast<const float4*>(st + r * kStagePad + cg * 8);
-                const float4 x1 = *reinterpret_cast<const float4*>(st + r * kStagePad + cg * 8 + 4);
-                float y[8] = {x0.x + bias[0], x0.y + bias[1], x0.z + bias[2], x0.w + bias[3],
-                              x1.x + bias[4], x1.y + bias[5], x1.z + bias[6], x1.w + bias[7]};
-                if (gelu) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] = gelu_tanh(y[e]);
-                }
-                uint4 w;
-                w.x = pack_bf16x2(y[0], y[1]);
-                w.y = pack_bf16x2(y[2], y[3]);
-                w.z = pack_bf16x2(y[4], y[5]);
-                w.w = pack_bf16x2(y[6], y[7]);
-                *reinterpret_cast<uint4*>(o + static_cast<long long>(r) * G.ldo) = w;
-              }
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(G.out) + o0;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + r_in;
-              if (r < rows) {
-                const float4 x = *reinterpret_cast<const float4*>(st + r * kStagePad + cg * 4);
-                float4 y = make_float4(x.x + bias[0], x.y + bias[1], x.z + bias[2], x.w + bias[3]);
-                if (resid)
-                  y = make_float4(resv[it].x + gate[0] * y.x, resv[it].y + gate[1] * y.y, resv[it].z + gate[2] * y.z,
-                                  resv[it].w + gate[3] * y.w);
-                *reinterpret_cast<float4*>(o + static_cast<long long>(r) * G.ldo) = y;
-              }
-            }
-          }
-        }
-        __syncwarp();
-      };
-
-      for (int c = 0; c < n_chunks; c += 2) {
-        if (resid && c + 1 < n_chunks) load_resv(c + 1, resv_b);
-        process_chunk(c, resv_a);
-        if (c + 1 < n_chunks) {
-          if (resid && c + 2 < n_chunks) load_resv(c + 2, resv_a);
-          process_chunk(c + 1, resv_b);
-        }
-      }
+      gemm_epilogue_tile<BN>(
+          G, tc.b, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, st, sbias, lane,
+          [&]() { mbar_wait(&tmem_full[acc], acc_phase); }, [&]() { if (lane == 0) mbar_arrive(&tmem_empty[acc]); });
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -393,7 +263,9 @@ int finish_op(GemmOp* op, const void* W, int N, int K, int epi, void* out, long 
   uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
   uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
   uint32_t box[2] = {BK, static_cast<uint32_t>(op->block_n)};
-  return encode_tmap_bf16(&op->tmB, W, 2, dims, strides, box);
+  TPDM_TRY(encode_tmap_bf16(&op->tmB, W, 2, dims, strides, box));
+  uint32_t box2[2] = {BK, 128};
+  return encode_tmap_bf16(&op->tmB2, W, 2, dims, strides, box2);
 }
 
 }  // namespace
@@ -476,6 +348,11 @@ int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {
     TPDM_CHECK(ops[i].block_n == ops[0].block_n, TPDM_ERR_ARG, "gemm_launch: grouped ops must share the N tile");
   }
   if (n_ops == 1) P.op[1] = ops[0];
+  // plain GEMMs with 256-wide N tiles go to the CTA-pair kernel (TPDM_GEMM_2CTA=0 forces the 1-CTA kernel)
+  static const bool pair = getenv("TPDM_GEMM_2CTA") == nullptr || atoi(getenv("TPDM_GEMM_2CTA")) != 0;
+  bool plain = ops[0].block_n == 256;
+  for (int i = 0; i < n_ops; ++i) plain = plain && ops[i].conv == 0;
+  if (pair && plain) return gemm2_launch(ops, n_ops, stream);
   return ops[0].block_n == 128 ? launch_impl<128>(P, stream) : launch_impl<256>(P, stream);
 }
 

@@ -62,6 +62,7 @@ enum GemmEpilogue : int {
 struct alignas(64) GemmOp {
   CUtensorMap tmA;  // normal: (K, rows_per_batch, batch) box (64,128,1); conv: (C, x, y, b) box (64, g, 128/g, 1)
   CUtensorMap tmB;  // (K, N) box (64, BN)
+  CUtensorMap tmB2; // (K, N) box (64, 128): half of a 256-wide N tile, for the CTA-pair kernel (gemm2_tcgen05.cu)
   int rows_per_batch, batch, N, K;
   int tiles_m_per_batch, tiles_n, num_tiles, block_n;
   int conv, conv_by, kb_per_tap, epi;  // conv: 0 plain, 1 conv3x3 forward, 2 conv3x3 weight gradient
@@ -87,6 +88,8 @@ int gemm_op_init_conv3x3(GemmOp* op, const void* X, int batch, int g, int C, con
 int gemm_op_init_conv3x3_wgrad(GemmOp* op, const void* dYt, const void* Xnchw, int samples, int g, int C, int M, float* dW);
 // one persistent launch over up to two ops (e.g. image stream + text stream)
 int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream);
+// CTA-pair (cta_group::2) kernel for plain GEMMs with 256-wide N tiles; gemm_launch dispatches to it
+int gemm2_launch(const GemmOp* ops, int n_ops, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------------------
 // joint attention (attention_tcgen05.cu)

@@ -123,6 +123,11 @@ if __name__ == "__main__":
         attn_case(1, 1357, 4, 64)
         attn_case(1, 1357, 4, 64, q_rows=1024)
         attn_case(2, 4429, 24, 64, 0, True)
+    if which == "gemm_k64":
+        for epi in (0, 1, 2, 3):
+            gemm_case(2, 4096, 1536, 64, epi, True)      # epilogue-bound: almost no MMA work
+        for epi in (0, 3):
+            gemm_case(2, 4096, 1536, 512, epi, True)
     if which == "gemm_epi":
         for epi in (0, 1, 2, 3):
             gemm_case(2, 4096, 1536, 1536, epi, True)

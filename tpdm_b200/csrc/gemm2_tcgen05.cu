@@ -6,11 +6,11 @@
 // CTA stages its own 128 rows of A but only HALF of the tile's W rows; tcgen05.mma.cta_group::2 (M = 256) reads A from
 // both CTAs and each half of B from the CTA that holds it: 64 + 64 B/clk per SM.  Stages shrink to 32 KB, so the ring is 6 deep.
 //
-// Roles per CTA (192 threads) are those of gemm_tcgen05.cu; differences:
+// Roles per CTA (320 threads: TMA warp, MMA warp, 8 epilogue warps) follow gemm_tcgen05.cu; differences:
 //   * TMA loads of BOTH CTAs complete on the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2, barrier address
 //     mapped with mapa); the leader's barrier expects one arrive.expect_tx per CTA;
 //   * only the leader's warp 1 issues MMAs; tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers;
-//   * the epilogue warps of both CTAs release the accumulator on the leader's tmem_empty barrier (count 8);
+//   * the epilogue warps of both CTAs release the accumulator on the leader's tmem_empty barrier (count 16);
 //   * TMEM is allocated / freed with the cta_group::2 forms by one warp of each CTA; cluster barriers bracket the kernel.
 #include <cuda_bf16.h>
 
@@ -25,13 +25,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN2 = 256;
 constexpr int BK = 64;
-constexpr int kStages2 = 6;
-constexpr int kThreads2 = 192;
+constexpr int kStages2 = 5;
+constexpr int kEpiWarps2 = 8;   // two warps per TMEM lane quarter, each draining half of the tile's columns
+constexpr int kThreads2 = 64 + 32 * kEpiWarps2;
 constexpr int kABytes2 = BM * BK * 2;
 constexpr int kBBytes2 = (BN2 / 2) * BK * 2;
 constexpr int kStageBytes2 = kABytes2 + kBBytes2;
 constexpr int kRing2 = kStages2 * kStageBytes2;
-constexpr int kEpi2 = 4 * 32 * kStagePad * 4 + 4 * 2 * BN2 * 4;
+constexpr int kEpi2 = kEpiWarps2 * 32 * kStagePad * 4 + kEpiWarps2 * 2 * (BN2 / 2) * 4;
 constexpr int kBarOff2 = kRing2 + kEpi2;
 constexpr int kSmem2 = kBarOff2 + 256 + 1024;
 
@@ -138,7 +139,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[i], 2 * kEpiWarps2);  // epilogue warps of both CTAs
     }
     fence_barrier_init();
   }
@@ -220,10 +221,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs; own 128 rows)
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs; own 128 rows)
+    // The epilogue, not the MMA, bounds the K = 1536 GEMMs (measured with K = 64: ~8.5 us per 128 x 256 tile with 4 warps
+    // against 7 us of MMA), so each TMEM lane quarter is drained by two warps: columns [0,128) and [128,256).
     const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
     float* st = epi_stage + (warp - 2) * 32 * kStagePad;
-    float* sbias = epi_stage + 4 * 32 * kStagePad + (warp - 2) * 2 * BN2;
+    float* sbias = epi_stage + kEpiWarps2 * 32 * kStagePad + (warp - 2) * 2 * (BN2 / 2);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters) {
@@ -232,7 +236,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
       const int n0 = tc.nt * BN2;
       const int row_base = tc.mtp * 2 * BM + static_cast<int>(rank) * BM + q * 32;
       gemm_epilogue_tile<BN2>(
-          G, tc.b, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2, st, sbias, lane,
+          G, tc.b, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2, st, sbias, lane, hh * (BN2 / 64), (hh + 1) * (BN2 / 64),
           [&]() { mbar_wait(&tmem_full[acc], acc_phase); },
           [&]() {
             if (lane == 0) mbar_arrive_cluster(map_to_cta(&tmem_empty[acc], 0));

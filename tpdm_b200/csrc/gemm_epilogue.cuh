@@ -14,11 +14,23 @@ constexpr int kStagePad = 36;  // floats per staged row: 16-byte aligned rows, c
 
 // `wait_accumulator()` blocks until the tile's accumulator is complete; `release_accumulator()` is called by the whole warp
 // once its last TMEM load has landed in registers.
+// The warp handles the 32-column chunks [c_begin, c_end) of the tile (all of them in the 1-CTA kernel; half of them in the
+// CTA-pair kernel, where two warps share each TMEM lane quarter).  sbias holds 2 * 32 * (c_end - c_begin) floats.
 template <int BN, typename WaitFn, typename ReleaseFn>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_idx, int row_base, int n0, uint32_t tmem_acc, float* st,
-                                                   float* sbias, int lane, WaitFn wait_accumulator, ReleaseFn release_accumulator) {
+                                                   float* sbias, int lane, int c_begin, int c_end, WaitFn wait_accumulator,
+                                                   ReleaseFn release_accumulator) {
   int n_chunks = (G.N - n0 + 31) / 32;
-  n_chunks = n_chunks > BN / 32 ? BN / 32 : n_chunks;
+  n_chunks = n_chunks > c_end ? c_end : n_chunks;
+  const int ncol = (c_end - c_begin) * 32;  // columns staged in sbias
+  if (n_chunks <= c_begin) {  // nothing to store for this warp (N tail), but the accumulator hand-shake must still happen
+    wait_accumulator();
+    tc_fence_after();
+    tc_fence_before();
+    __syncwarp();
+    release_accumulator();
+    return;
+  }
       int rows = G.rows_per_batch - row_base;
       rows = rows > 32 ? 32 : rows;
       const bool f32_out = G.epi == EPI_BIAS_F32 || G.epi == EPI_GATE_RESIDUAL;
@@ -48,24 +60,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
       };
       // bias / gate of the tile's columns: fetched once per tile into shared memory while the MMA is still running (loading
       // them per 32-column chunk put an L2 round trip on the critical path of every chunk)
-      for (int k = lane * 4; k < BN; k += 128) {
-        const int col = n0 + k;
+      for (int k = lane * 4; k < ncol; k += 128) {
+        const int col = n0 + c_begin * 32 + k;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = b4;
         if (col < G.N) {
           if (G.bias) b4 = *reinterpret_cast<const float4*>(G.bias + col);
           if (resid) g4 = *reinterpret_cast<const float4*>(gate_row + col);
         }
         *reinterpret_cast<float4*>(sbias + k) = b4;
-        *reinterpret_cast<float4*>(sbias + BN + k) = g4;
+        *reinterpret_cast<float4*>(sbias + ncol + k) = g4;
       }
       __syncwarp();
       float4 resv_a[8], resv_b[8];
       if (resid) {
         if (lane < rows) {
           const float* o = reinterpret_cast<const float*>(G.out) + tile_o0 + static_cast<long long>(lane) * G.ldo;
-          for (int c = 1; c < n_chunks; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(o + c * 32));
+          for (int c = c_begin + 1; c < n_chunks; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(o + c * 32));
         }
-        load_resv(0, resv_a);
+        load_resv(c_begin, resv_a);
       }
       wait_accumulator();
       tc_fence_after();
@@ -76,7 +88,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
         const long long o0 = tile_o0 + c * 32 + cg * vec;
         float bias[8], gate[4];
         {
-          const float* sb = sbias + c * 32 + cg * vec;
+          const float* sb = sbias + (c - c_begin) * 32 + cg * vec;
           const float4 b0 = *reinterpret_cast<const float4*>(sb);
           bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
           if (!f32_out) {
@@ -85,7 +97,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
           } else {
             bias[4] = bias[5] = bias[6] = bias[7] = 0.f;
           }
-          const float4 g4 = *reinterpret_cast<const float4*>(sb + BN);
+          const float4 g4 = *reinterpret_cast<const float4*>(sb + ncol);
           gate[0] = g4.x; gate[1] = g4.y; gate[2] = g4.z; gate[3] = g4.w;
         }
         uint32_t v[32];
@@ -143,7 +155,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
         __syncwarp();
       };
 
-      for (int c = 0; c < n_chunks; c += 2) {
+      for (int c = c_begin; c < n_chunks; c += 2) {
         if (resid && c + 1 < n_chunks) load_resv(c + 1, resv_b);
         process_chunk(c, resv_a);
         if (c + 1 < n_chunks) {

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       const int n0 = tc.nt * BN;
       const int row_base = tc.mt * BM + q * 32;
       gemm_epilogue_tile<BN>(
-          G, tc.b, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, st, sbias, lane,
+          G, tc.b, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, st, sbias, lane, 0, BN / 32,
           [&]() { mbar_wait(&tmem_full[acc], acc_phase); }, [&]() { if (lane == 0) mbar_arrive(&tmem_empty[acc]); });
       if (++acc == 2) {
         acc = 0;

@@ -61,7 +61,7 @@ struct AttnSmem {
 template <int DP>
 __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attention_tcgen05_kernel(const __grid_constant__ AttnOp A) {
   using L = AttnSmem<DP>;
-  if (A.skip != nullptr && *A.skip != 0) return;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
     }
     fence_barrier_init();
   }
+  pdl_wait();
+  if (A.skip != nullptr && *A.skip != 0) return;
   if (warp == 2) {
     tmem_alloc<L::kTmemCols>(tmem_slot);
     tmem_relinquish();
@@ -138,8 +140,8 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
         }
       }
     }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp == 1 || warp == 3) {
+    // ---------------------------------------------------------------- MMA issuers (warp 1: S = Q K^T, warp 3: O += P V)
     constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kHT, false);
     constexpr uint32_t idesc_pv = make_idesc_bf16(kQT, DP, true);
     const uint32_t q_base = smem_u32(smem + L::kQOff);
@@ -185,11 +187,15 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       __syncwarp();
     };
 
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    for (int i = 0; i < n_half; ++i) {
-      if (i + 1 < n_half) issue_qk(i + 1);
-      issue_pv(i);
+    // QK and PV are issued by TWO warps.  Every tcgen05.mma costs the issuing thread ~150 cycles before the next one can
+    // go out, however small it is, and with one issuer the 16 MMAs per 128 keys (8 QK + 8 PV) -- not the softmax -- paced
+    // this kernel (every measured variant fits that model, see the list at the top).  All hand-offs between the two
+    // streams go through mbarriers (s_free / p_full / pv_done), none relies on a common issue order.
+    if (warp == 1) {
+      mbar_wait(q_full, 0);
+      for (int i = 0; i < n_half; ++i) issue_qk(i);
+    } else {
+      for (int i = 0; i < n_half; ++i) issue_pv(i);
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- softmax / correction / epilogue
@@ -395,7 +401,7 @@ int attn_launch_impl(const AttnOp& op, cudaStream_t stream) {
   dim3 grid(op.q_tiles, op.H, op.Bt);
   const double q_rows = op.q_tiles * kQT < op.S ? op.q_tiles * kQT : op.S;
   prof_begin(1, 4.0 * op.Bt * op.H * q_rows * op.S * op.head_dim, stream);
-  joint_attention_tcgen05_kernel<DP><<<grid, kAttnThreads, AttnSmem<DP>::kTotal, stream>>>(op);
+  TPDM_CUDA_OK(launch_pdl(joint_attention_tcgen05_kernel<DP>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
   prof_end(stream);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());

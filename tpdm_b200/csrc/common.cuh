@@ -30,6 +30,13 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Programmatic dependent launch (host side: launch_pdl in host.h).  A kernel lets the next grid in the stream start
+// being scheduled as soon as every CTA of this one has been launched (launch_dependents at the very top), and it must
+// itself pass pdl_wait() -- which returns once ALL earlier grids have completed and their stores are visible --
+// before it touches global memory or allocates TMEM.  Launch latency, barrier set-up and descriptor prefetch of kernel
+// n+1 then overlap the tail of kernel n.  Both are no-ops for a grid that was launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 

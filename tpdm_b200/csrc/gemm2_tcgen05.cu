@@ -111,7 +111,7 @@ __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_bf16_tcgen05_kernel(const __grid_constant__ Gemm2Params P) {
-  if (P.skip != nullptr && *P.skip != 0) return;  // uniform over the grid, so both CTAs of a pair leave together
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + kRing2);
@@ -143,6 +143,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
     }
     fence_barrier_init();
   }
+  pdl_wait();
+  if (P.skip != nullptr && *P.skip != 0) return;  // uniform over the grid, so both CTAs of a pair leave together
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
@@ -282,7 +284,7 @@ int gemm2_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {
   const int max_clusters = num_sms() / 2;
   const int clusters = P.total_tiles < max_clusters ? P.total_tiles : max_clusters;
   prof_begin(0, flops, stream);
-  gemm2_bf16_tcgen05_kernel<<<2 * clusters, kThreads2, kSmem2, stream>>>(P);
+  TPDM_CUDA_OK(launch_pdl(gemm2_bf16_tcgen05_kernel, dim3(2 * clusters), dim3(kThreads2), kSmem2, stream, P));
   prof_end(stream);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());

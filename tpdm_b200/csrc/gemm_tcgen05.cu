@@ -69,7 +69,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(const __grid_constant__ GemmParams P) {
   using L = GemmSmem<BN>;
-  if (P.skip != nullptr && *P.skip != 0) return;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + L::kRing);
@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
     }
     fence_barrier_init();
   }
+  pdl_wait();
+  if (P.skip != nullptr && *P.skip != 0) return;
   if (warp == 2) {
     tmem_alloc<2 * BN>(tmem_slot);
     tmem_relinquish();
@@ -233,7 +235,7 @@ int launch_impl(const GemmParams& P, cudaStream_t stream) {
   double flops = 0;
   for (int i = 0; i < P.n_ops; ++i) flops += 2.0 * P.op[i].batch * P.op[i].rows_per_batch * static_cast<double>(P.op[i].N) * P.op[i].K;
   prof_begin(0, flops, stream);
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, GemmSmem<BN>::kTotal, stream>>>(P);
+  TPDM_CUDA_OK(launch_pdl(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(kGemmThreads), GemmSmem<BN>::kTotal, stream, P));
   prof_end(stream);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());

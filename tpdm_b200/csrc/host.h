@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <utility>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -44,6 +45,23 @@ void prof_end(cudaStream_t s);
 // denoising step enqueued speculatively after the trajectory has finished costs only empty launches.
 void set_skip_flag(const int* device_flag);
 const int* skip_flag();
+
+// Launch with programmatic stream serialization (see pdl_wait in common.cuh); TPDM_PDL=0 turns the attribute off.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // bf16 tiled tensor map with 128-byte swizzle.  dims/strides innermost first; strides (bytes) for dims 1..rank-1.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

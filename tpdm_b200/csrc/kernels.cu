@@ -252,6 +252,8 @@ __device__ __forceinline__ float4 ld4_stream(const float* p) {
 
 template <int VPL>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant__ LnParams P) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (P.skip != nullptr && *P.skip != 0) return;
   extern __shared__ float ln_mod[];  // [D] shift, [D] scale
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -719,11 +721,11 @@ int k_ln_modulate(const LnSeg* segs, int nseg, int D, cudaStream_t s) {
   const size_t smem = static_cast<size_t>(2) * D * sizeof(float);
   TPDM_CHECK(smem <= 48 * 1024, TPDM_ERR_SHAPE, "ln_modulate: D=%d too large", D);
   if (D == 1536)
-    ln_modulate_kernel<12><<<grid, 256, smem, s>>>(P);
+    TPDM_CUDA_OK(launch_pdl(ln_modulate_kernel<12>, dim3(grid), dim3(256), smem, s, P));
   else if (D == 384)
-    ln_modulate_kernel<3><<<grid, 256, smem, s>>>(P);
+    TPDM_CUDA_OK(launch_pdl(ln_modulate_kernel<3>, dim3(grid), dim3(256), smem, s, P));
   else
-    ln_modulate_kernel<0><<<grid, 256, smem, s>>>(P);
+    TPDM_CUDA_OK(launch_pdl(ln_modulate_kernel<0>, dim3(grid), dim3(256), smem, s, P));
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // tpdm_b200 -- error reporting, device queries and TMA descriptor encoding shared by the library.
 #include <stdarg.h>
 
@@ -28,6 +29,13 @@ void set_skip_flag(const int* f) { g_skip = f; }
 const int* skip_flag() { return g_skip; }
 
 static std::atomic<long long> g_launches{0};
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("TPDM_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 namespace {

@@ -204,6 +204,17 @@ int tpdm_tpm_train_backward(tpdm_tpm_trainer* t, const float* dz, void* stream);
 int tpdm_ppo_clip_loss(const float* alpha_beta, const float* sigmas, const float* old_logprobs, const float* advantages,
                        int mb, int T, float min_sigma, float epsilon, int relative, float cliprange, float tpm_epsilon,
                        float* new_logprobs, float* dz, float* stats4, void* stream);
+/* Reward shaping of one RLOO rollout on the device (replaces the Python loops of modeling_sd3_pnt.py:828-841 and :875-901 and
+ * the tensor code of rloo_trainer.py:447-461).  alphas / betas / sigmas [batch][steps] fp32 and masks [batch][steps] int32 as
+ * the sampler leaves them; last_rewards [batch] (NULL: scores = 0).  Outputs (each may be NULL): kl [batch][steps] =
+ * KL(Beta(alpha,beta) || reference) with 0 at masked steps -- the reference is Beta(get_ref_beta(sigma_in, ref_steps)) when
+ * `relative`, else Beta(1.4, 11.2); scores [batch] = discounted mean of last_reward (gamma); rlhf_reward = scores -
+ * kl_coef * (sum, or mean when mean_kl) of kl; advantages = leave-one-out over the rloo_k repeats (layout: repeats x
+ * prompts).  batch <= 1024. */
+int tpdm_rollout_shaping(const float* alphas, const float* betas, const float* sigmas, const int* masks,
+                         const float* last_rewards, int batch, int steps, int relative, int ref_steps, float gamma,
+                         float kl_coef, int mean_kl, int rloo_k, float* kl, float* scores, float* rlhf_reward,
+                         float* advantages, void* stream);
 /* g = grads * grad_scale; clip to max_grad_norm (<= 0: off); AdamW (decoupled weight decay); non-finite norm skips the
  * update; the first bf16_n parameters are mirrored to bf16_copy.  scratch_sumsq: 1 double on the device (holds |g|^2 after). */
 int tpdm_adamw_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,

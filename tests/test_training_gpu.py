@@ -152,3 +152,44 @@ def test_rloo_update_end_to_end_tiny():
     assert torch.equal(t_before, w.agent_model.transformer.proj_out.weight)
     out = w.sample(dict(data, predict=True))
     assert torch.isfinite(out["latents"]).all()
+
+
+@pytest.mark.parametrize("relative,mean_kl", [(True, False), (False, True)])
+def test_rollout_shaping_matches_reference_math(relative, mean_kl):
+    """Next-row (f)2: KL to the reference schedule, discounted score, rlhf reward and RLOO advantage on the device vs the
+    reference's own get_ref_beta (extracted, golden-pinned in test_oracle) + torch.distributions + the restated loops."""
+    from oracle import sd3_oracle as O
+    from tpdm_b200.rloo import shape_rollout
+
+    g = torch.Generator().manual_seed(11)
+    k, prompts, T = 4, 3, 9
+    B = k * prompts
+    alphas = 1.0 + 6.0 * torch.rand(B, T, generator=g)
+    betas = 1.0 + 6.0 * torch.rand(B, T, generator=g)
+    ratios = 0.6 + 0.35 * torch.rand(B, T, generator=g)      # keeps sigma above the range where the reference Beta degenerates
+    sigmas = torch.cumprod(ratios, 1)                       # sigma_next after each step
+    lengths = torch.randint(1, T + 1, (B,), generator=g)
+    masks = torch.arange(T)[None, :] >= lengths[:, None]    # True = step not executed
+    last = torch.randn(B, generator=g)
+    gamma, kl_coef = 0.97, 0.05
+    out = shape_rollout(dict(alphas=alphas.cuda(), betas=betas.cuda(), sigmas=sigmas.cuda(), prob_masks=masks.cuda()), last.cuda(),
+                        relative=relative, gamma=gamma, kl_coef=kl_coef, mean_kl=mean_kl, rloo_k=k)
+    sig_in = torch.nn.functional.pad(sigmas[:, :-1], (1, 0), value=1.0)
+    if relative:
+        ra, rb = O.get_ref_beta(sig_in)
+    else:
+        ra, rb = torch.full_like(alphas, 1.4), torch.full_like(alphas, 11.2)
+    kl = torch.distributions.kl_divergence(torch.distributions.Beta(alphas.double(), betas.double()),
+                                           torch.distributions.Beta(ra.double(), rb.double())).float()
+    kl = torch.where(masks, torch.zeros_like(kl), kl)
+    scores = torch.tensor([O.discounted_reward(float(last[i]), int(lengths[i]) - 1, gamma) for i in range(B)])
+    non_score = (-kl_coef * kl).mean(1) if mean_kl else (-kl_coef * kl).sum(1)
+    rlhf = scores + non_score
+    adv = O.rloo_advantage(rlhf, k)
+    assert torch.allclose(out["kl"].cpu(), kl, rtol=2e-4, atol=2e-5)
+    assert torch.allclose(out["scores"].cpu(), scores, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(out["rlhf_reward"].cpu(), rlhf, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["advantages"].cpu(), adv, rtol=1e-4, atol=2e-5)
+    # the same KL through the reference's own closed form (train_utilis.py:6-20, argument order as the reference passes it)
+    kl2 = O.get_kl_beta(betas.double(), alphas.double(), rb.double(), ra.double()).float()
+    assert torch.allclose(torch.where(masks, torch.zeros_like(kl2), kl2), kl, rtol=1e-4, atol=1e-5)

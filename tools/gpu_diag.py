@@ -123,6 +123,30 @@ if __name__ == "__main__":
         attn_case(1, 1357, 4, 64)
         attn_case(1, 1357, 4, 64, q_rows=1024)
         attn_case(2, 4429, 24, 64, 0, True)
+    if which == "gemm_ncu":   # one launch per SD3-medium block GEMM shape, for an `ncu --set full` capture
+        gemm_case(2, 4429, 4608, 1536, 0)
+        gemm_case(2, 4429, 6144, 1536, 2)
+        gemm_case(2, 4429, 1536, 6144, 3)
+        gemm_case(2, 4429, 1536, 1536, 3)
+    if which == "ln":
+        for (batch, rows) in ((2, 4096), (2, 333)):
+            D = 1536
+            x = torch.randn(batch, rows, D, device="cuda")
+            mod = torch.randn(batch, 2 * D, device="cuda") * 0.1
+            out = torch.empty(batch, rows, D, device="cuda", dtype=torch.bfloat16)
+            fn = lambda: L.check(lib.tpdm_ln_modulate(L.ptr(x), L.ptr(mod), L.ptr(mod) + 4 * D, 2 * D, L.ptr(out), batch, rows, D,
+                                                        torch.cuda.current_stream().cuda_stream))
+            fn()
+            ref = torch.nn.functional.layer_norm(x, (D,), eps=1e-6) * (1 + mod[:, None, D:]) + mod[:, None, :D]
+            big = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
+            ms = timeit(fn, 20)
+            def cold():
+                big.zero_()
+                fn()
+            ms_cold = timeit(cold, 10) - timeit(lambda: big.zero_(), 10)
+            gb = batch * rows * D * 6 / 1e9
+            print(f"ln batch={batch} rows={rows}: rel={rel(out, ref):.2e}  warm {ms*1e3:.1f} us ({gb/ms*1e3:.0f} GB/s)  "
+                  f"after L2 flush {ms_cold*1e3:.1f} us ({gb/ms_cold*1e3:.0f} GB/s)", flush=True)
     if which == "gemm_k64":
         for epi in (0, 1, 2, 3):
             gemm_case(2, 4096, 1536, 64, epi, True)      # epilogue-bound: almost no MMA work

@@ -66,6 +66,8 @@ EXPORTS = {
     "tpdm_tpm_trainer_bind": (C.c_int, [vp, vp, vp, vp]),
     "tpdm_tpm_train_forward": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "tpdm_tpm_train_backward": (C.c_int, [vp, vp, vp]),
+    "tpdm_rollout_shaping": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                       vp, vp, vp, vp, vp]),
     "tpdm_ppo_clip_loss": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]),
     "tpdm_adamw_step": (C.c_int, [vp, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
                                   C.c_float, vp, vp, C.c_longlong, vp]),

@@ -194,20 +194,40 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
       w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
     }
     const float bs = bias[d];
-    for (int t = 0; t < kPatchTok; ++t) {
-      const int n = n0 + t;
-      const int ty = n / gw, tx = n - ty * gw;
-      float acc = bs;
-      const float* ip = in_s + t * KK;
+    // Four tokens at a time: their four pos-table loads are issued together before the FMA block (one exposed global-load
+    // latency per token made the first version latency-bound at 107 us for SD3-medium), and the four accumulator chains
+    // are independent.  k_patchify guarantees C*4 == 64 and N % kPatchTok == 0.
+    for (int t0 = 0; t0 < kPatchTok; t0 += 4) {
+      float pv[4], acc[4];
 #pragma unroll
-      for (int k = 0; k < 64; ++k) acc = fmaf(w[k], ip[k], acc);
-      acc += pos[(static_cast<long long>(top + ty) * pos_max + left + tx) * D + d];
-      for (int r = 0; r < dup; ++r) {
-        const long long o = (static_cast<long long>(bl + r * Bl) * N + n) * D + d;
-        x[o] = acc;
-        if (h1_out) h1_out[o] = acc;
+      for (int u = 0; u < 4; ++u) {
+        const int n = n0 + t0 + u;
+        const int ty = n / gw, tx = n - ty * gw;
+        pv[u] = pos[(static_cast<long long>(top + ty) * pos_max + left + tx) * D + d];
+        acc[u] = bs;
       }
-      if (tpm_x) tpm_x[(static_cast<long long>(bl) * N + scramble_pixel(n, gw)) * (2 * D) + d] = __float2bfloat16(acc);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float4 v = *reinterpret_cast<const float4*>(in_s + (t0 + u) * 64 + 4 * k);  // broadcast LDS.128
+          acc[u] = fmaf(w[4 * k], v.x, acc[u]);
+          acc[u] = fmaf(w[4 * k + 1], v.y, acc[u]);
+          acc[u] = fmaf(w[4 * k + 2], v.z, acc[u]);
+          acc[u] = fmaf(w[4 * k + 3], v.w, acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int n = n0 + t0 + u;
+        const float r_ = acc[u] + pv[u];
+        for (int r = 0; r < dup; ++r) {
+          const long long o = (static_cast<long long>(bl + r * Bl) * N + n) * D + d;
+          x[o] = r_;
+          if (h1_out) h1_out[o] = r_;
+        }
+        if (tpm_x) tpm_x[(static_cast<long long>(bl) * N + scramble_pixel(n, gw)) * (2 * D) + d] = __float2bfloat16(r_);
+      }
     }
   }
 }
@@ -499,10 +519,13 @@ __global__ void __launch_bounds__(256) gn_mod_silu_kernel(const float* __restric
   a[i] = silu_f(v);
 }
 
-constexpr int kC2Pix = 8;
-__global__ void conv3x3_s2_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
-                                  float* __restrict__ y, int g, int C) {
-  extern __shared__ float in_s[];  // [3][2*kC2Pix+1][C]
+constexpr int kC2Pix = 4;
+// Block = kC2Pix output pixels of one row; thread = (input-channel half, output channel).  The two halves are summed
+// through shared memory.  512 blocks of 2*C threads for a 64x64 input: the first version (8 pixels, C threads, scalar
+// LDS) ran 128 blocks and was latency-bound at 125 us.
+__global__ void __launch_bounds__(256) conv3x3_s2_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int g, int C) {
+  extern __shared__ __align__(16) float in_s[];  // [3][2*kC2Pix+1][C], then [kC2Pix][C] partial sums
   const int go = g / 2;
   const int b = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * kC2Pix;
   const int cols = 2 * kC2Pix + 1;
@@ -512,27 +535,45 @@ __global__ void conv3x3_s2_kernel(const float* __restrict__ a, const float* __re
     in_s[i] = (iy >= 0 && iy < g && ix >= 0 && ix < g) ? a[((static_cast<long long>(b) * g + iy) * g + ix) * C + c] : 0.f;
   }
   __syncthreads();
-  const int oc = threadIdx.x;
+  const int oc = threadIdx.x % C, half = threadIdx.x / C;
+  const int cb = half * (C / 2), ce = cb + C / 2;
   float acc[kC2Pix];
 #pragma unroll
-  for (int p = 0; p < kC2Pix; ++p) acc[p] = bias[oc];
+  for (int p = 0; p < kC2Pix; ++p) acc[p] = half == 0 ? bias[oc] : 0.f;
   for (int tap = 0; tap < 9; ++tap) {
     const int ky = tap / 3, kx = tap % 3;
     const float* wp = w + static_cast<long long>(tap) * C * C + oc;
     const float* ip = in_s + (ky * cols + kx) * C;
-    for (int c0 = 0; c0 < C; c0 += 8) {
+    for (int c0 = cb; c0 < ce; c0 += 8) {
       float wv[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) wv[u] = wp[static_cast<long long>(c0 + u) * C];  // 8 independent (coalesced over oc) loads in flight
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-#pragma unroll
-        for (int p = 0; p < kC2Pix; ++p) acc[p] = fmaf(wv[u], ip[2 * p * C + c0 + u], acc[p]);
+      for (int p = 0; p < kC2Pix; ++p) {
+        const float4 i0 = *reinterpret_cast<const float4*>(ip + 2 * p * C + c0);  // broadcast LDS.128
+        const float4 i1 = *reinterpret_cast<const float4*>(ip + 2 * p * C + c0 + 4);
+        acc[p] = fmaf(wv[0], i0.x, acc[p]);
+        acc[p] = fmaf(wv[1], i0.y, acc[p]);
+        acc[p] = fmaf(wv[2], i0.z, acc[p]);
+        acc[p] = fmaf(wv[3], i0.w, acc[p]);
+        acc[p] = fmaf(wv[4], i1.x, acc[p]);
+        acc[p] = fmaf(wv[5], i1.y, acc[p]);
+        acc[p] = fmaf(wv[6], i1.z, acc[p]);
+        acc[p] = fmaf(wv[7], i1.w, acc[p]);
+      }
     }
   }
+  float* part = in_s + 3 * cols * C;
+  if (half == 1) {
 #pragma unroll
-  for (int p = 0; p < kC2Pix; ++p)
-    if (ox0 + p < go) y[((static_cast<long long>(b) * go + oy) * go + ox0 + p) * C + oc] = acc[p];
+    for (int p = 0; p < kC2Pix; ++p) part[p * C + oc] = acc[p];
+  }
+  __syncthreads();
+  if (half == 0) {
+#pragma unroll
+    for (int p = 0; p < kC2Pix; ++p)
+      if (ox0 + p < go) y[((static_cast<long long>(b) * go + oy) * go + ox0 + p) * C + oc] = acc[p] + part[p * C + oc];
+  }
 }
 
 // adaptive_avg_pool2d(16,16) -> global max -> fc1 -> SiLU -> fc2 -> exp + eps.  One block of 1024 threads per sample:
@@ -567,21 +608,37 @@ __global__ void __launch_bounds__(1024) tpm_tail_kernel(const float* __restrict_
     pooled[t] = m;
   }
   __syncthreads();
+  // fc1: the 8 thread groups split the input channels (16 each), partial sums meet in shared memory; fc2: one warp per
+  // output, lanes split the 128 hidden units.  (One thread per output walked 32 / 128 dependent-latency loads.)
+  {
+    float acc = 0.f;
+    if (t < 128) {
+      const int cpg = C / 8;  // C % 32 == 0 is checked by k_tpm_tail
+      const float* wr = fc1_w + t * C + grp * cpg;
+#pragma unroll 4
+      for (int c = 0; c < cpg; c += 4) {
+        const float4 w4 = ld4(wr + c);
+        const float* pc = pooled + grp * cpg + c;
+        acc = fmaf(w4.x, pc[0], fmaf(w4.y, pc[1], fmaf(w4.z, pc[2], fmaf(w4.w, pc[3], acc))));
+      }
+    }
+    __syncthreads();  // everyone is done reading part[][] from the pooling phase
+    part[grp][t] = acc;
+  }
+  __syncthreads();
   if (threadIdx.x < 128) {
     float acc = fc1_b[t];
-    const float4* wr = reinterpret_cast<const float4*>(fc1_w + t * C);
-#pragma unroll 8
-    for (int c = 0; c < C / 4; ++c) {
-      const float4 w4 = wr[c];
-      acc = fmaf(w4.x, pooled[4 * c], fmaf(w4.y, pooled[4 * c + 1], fmaf(w4.z, pooled[4 * c + 2], fmaf(w4.w, pooled[4 * c + 3], acc))));
-    }
+#pragma unroll
+    for (int g8 = 0; g8 < 8; ++g8) acc += part[g8][t];
     hid[t] = silu_f(acc);
   }
   __syncthreads();
-  if (threadIdx.x < 2) {
-    float acc = fc2_b[t];
-    for (int j = 0; j < 128; ++j) acc = fmaf(fc2_w[t * 128 + j], hid[j], acc);
-    alpha_beta[b * 2 + t] = expf(acc) + eps;
+  if (threadIdx.x < 64) {
+    const int o = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 w4 = ld4(fc2_w + o * 128 + lane * 4);
+    float acc = w4.x * hid[lane * 4] + w4.y * hid[lane * 4 + 1] + w4.z * hid[lane * 4 + 2] + w4.w * hid[lane * 4 + 3];
+    acc = warp_sum(acc);
+    if (lane == 0) alpha_beta[b * 2 + o] = expf(acc + fc2_b[o]) + eps;
   }
 }
 
@@ -802,8 +859,9 @@ int k_conv3x3_s2(const float* a, const float* w, const float* bias, float* y, in
   TPDM_CHECK(C <= 1024 && C % 8 == 0 && g % 2 == 0, TPDM_ERR_SHAPE, "conv3x3_s2: unsupported shape");
   const int go = g / 2;
   dim3 grid((go + kC2Pix - 1) / kC2Pix, go, B);
-  const size_t smem = static_cast<size_t>(3) * (2 * kC2Pix + 1) * C * sizeof(float);
-  conv3x3_s2_kernel<<<grid, C, smem, s>>>(a, w, bias, y, g, C);
+  TPDM_CHECK(C % 16 == 0 && 2 * C <= 256, TPDM_ERR_SHAPE, "conv3x3_s2: channels %d must be a multiple of 16 and <= 128", C);
+  const size_t smem = static_cast<size_t>(3 * (2 * kC2Pix + 1) + kC2Pix) * C * sizeof(float);
+  conv3x3_s2_kernel<<<grid, 2 * C, smem, s>>>(a, w, bias, y, g, C);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;
@@ -811,7 +869,7 @@ int k_conv3x3_s2(const float* a, const float* w, const float* bias, float* y, in
 
 int k_tpm_tail(const float* y2, int B, int go, int C, const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b,
                float eps, float* alpha_beta, cudaStream_t s) {
-  TPDM_CHECK(C <= 128, TPDM_ERR_SHAPE, "tpm_tail: conv_out_channels %d > 128", C);
+  TPDM_CHECK(C <= 128 && C % 32 == 0, TPDM_ERR_SHAPE, "tpm_tail: conv_out_channels %d must be a multiple of 32, <= 128", C);
   tpm_tail_kernel<<<B, 1024, 0, s>>>(y2, go, C, fc1_w, fc1_b, fc2_w, fc2_b, eps, alpha_beta);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());

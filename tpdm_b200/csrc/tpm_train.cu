@@ -482,6 +482,83 @@ int check_trainer(const tpdm_tpm_trainer* t) {
 
 }  // namespace
 
+namespace {
+
+// Reward shaping of one RLOO rollout, one thread per rollout (batch <= 1024), replacing three host-side Python loops:
+//   kl[b][t]   = KL(Beta(alpha, beta) || reference Beta) with the reference schedule's Beta(get_ref_beta(sigma_in)) when
+//                `relative`, else Beta(1.4, 11.2); 0 at masked steps        (modeling_sd3_pnt.py:875-901,
+//                reference_distributions.py:9-19, torch.distributions.kl._kl_beta_beta)
+//   score[b]   = mean_{j<=last} last_reward * gamma^(last-j), last = last unmasked step      (modeling_sd3_pnt.py:828-841)
+//   rlhf[b]    = score - kl_coef * (sum | mean)_t kl                                           (rloo_trainer.py:447-451)
+//   adv[b]     = rlhf - (sum over the rloo_k repeats of the same prompt - rlhf) / (rloo_k - 1)  (rloo_trainer.py:458-461)
+// sigma_in[t] = 1 for t = 0, sigmas[t-1] after (F.pad(sigmas[..., :-1], (1, 0), value=1.0)).
+struct ShapeArgs {
+  const float *alphas, *betas, *sigmas, *last_rewards;
+  const int* masks;
+  float *kl, *scores, *rlhf, *adv;
+  int B, T, relative, ref_steps, mean_kl, rloo_k;
+  float gamma, kl_coef;
+};
+
+__device__ double log_beta_fn(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
+
+__global__ void rollout_shaping_kernel(ShapeArgs a) {
+  __shared__ float rl[1024];
+  const int b = threadIdx.x;
+  const float ex = 2.718281828459045f;  // reference_distributions.py:7, ex = math.exp(1); python scalar * fp32 tensor -> fp32
+  if (b < a.B) {
+    double kl_sum = 0.0;
+    int last = -1;
+    for (int t = 0; t < a.T; ++t) {
+      const int i = b * a.T + t;
+      double kl = 0.0;
+      if (a.masks[i] == 0) {
+        last = t;
+        const double al = a.alphas[i], be = a.betas[i];
+        double ra = 1.4, rb = 11.2;
+        if (a.relative) {
+          // float arithmetic on purpose: the reference evaluates get_ref_beta on fp32 tensors
+          const float s1 = t == 0 ? 1.0f : a.sigmas[i - 1];
+          const float t1 = s1 / (ex + (1.0f - ex) * s1);
+          const float t2 = fmaxf(t1 - static_cast<float>(1.0 / a.ref_steps), 1e-3f);
+          const float s2 = ex / (ex + 1.0f / t2 - 1.0f);
+          const float mode = s2 / s1;
+          ra = mode * 18.0f + 1.0f;
+          rb = (1.0f - mode) * 18.0f + 1.0f;
+        }
+        const double psi_ab = digamma_d(al + be);
+        kl = log_beta_fn(ra, rb) - log_beta_fn(al, be) + (al - ra) * digamma_d(al) + (be - rb) * digamma_d(be) +
+             (ra - al + rb - be) * psi_ab;
+      }
+      if (a.kl) a.kl[i] = static_cast<float>(kl);
+      kl_sum += kl;
+    }
+    float score = 0.f;
+    if (a.last_rewards != nullptr && last >= 0) {
+      double acc = 0.0, w = 1.0;
+      for (int j = 0; j <= last; ++j) {
+        acc += w;
+        w *= a.gamma;
+      }
+      score = static_cast<float>(a.last_rewards[b] * acc / (last + 1));
+    }
+    const float non_score = -a.kl_coef * static_cast<float>(a.mean_kl ? kl_sum / a.T : kl_sum);
+    const float r = score + non_score;
+    if (a.scores) a.scores[b] = score;
+    if (a.rlhf) a.rlhf[b] = r;
+    rl[b] = r;
+  }
+  __syncthreads();
+  if (b < a.B && a.adv != nullptr) {
+    const int prompts = a.B / a.rloo_k, p = b % prompts;  // layout: rloo_k repeats x prompts
+    float sum = 0.f;
+    for (int k = 0; k < a.rloo_k; ++k) sum += rl[k * prompts + p];
+    a.adv[b] = rl[b] - (sum - rl[b]) / static_cast<float>(a.rloo_k - 1);
+  }
+}
+
+}  // namespace
+
 extern "C" {
 
 int tpdm_tpm_param_offsets(int D, int C1, long long* out13) {
@@ -612,6 +689,22 @@ int tpdm_ppo_clip_loss(const float* alpha_beta, const float* sigmas, const float
   TPDM_CHECK(mb > 0 && mb <= 1024 && T > 0, TPDM_ERR_SHAPE, "tpdm_ppo_clip_loss: micro-batch %d outside [1,1024]", mb);
   PpoArgs a{alpha_beta, sigmas, old_logprobs, advantages, new_logprobs, dz, stats4, mb, T, relative, min_sigma, epsilon, cliprange, tpm_epsilon};
   ppo_clip_kernel<<<1, ((mb + 31) / 32) * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch();
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int tpdm_rollout_shaping(const float* alphas, const float* betas, const float* sigmas, const int* masks, const float* last_rewards,
+                         int batch, int steps, int relative, int ref_steps, float gamma, float kl_coef, int mean_kl, int rloo_k, float* kl,
+                         float* scores, float* rlhf_reward, float* advantages, void* stream) {
+  TPDM_CHECK(alphas && betas && sigmas && masks, TPDM_ERR_ARG, "tpdm_rollout_shaping: null argument");
+  TPDM_CHECK(batch > 0 && batch <= 1024 && steps > 0, TPDM_ERR_SHAPE, "tpdm_rollout_shaping: batch %d outside [1,1024]", batch);
+  TPDM_CHECK(ref_steps > 0, TPDM_ERR_ARG, "tpdm_rollout_shaping: ref_steps must be positive");
+  TPDM_CHECK(advantages == nullptr || (rloo_k >= 2 && batch % rloo_k == 0), TPDM_ERR_ARG,
+             "tpdm_rollout_shaping: batch %d is not a multiple of rloo_k %d (>= 2)", batch, rloo_k);
+  ShapeArgs a{alphas, betas, sigmas, last_rewards, masks, kl, scores, rlhf_reward, advantages, batch, steps, relative, ref_steps,
+                    mean_kl, rloo_k, gamma, kl_coef};
+  rollout_shaping_kernel<<<1, ((batch + 31) / 32) * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

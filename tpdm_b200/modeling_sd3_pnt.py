@@ -388,15 +388,9 @@ class SD3PredictNextTimeStepModelRLOOWrapper(nn.Module):
             fix_tembs=outputs["tembs"])["logprobs"]
 
     def kl_divergence(self, outputs: CustomDiffusionModelOutput):
-        """:875-901, vectorised: KL(Beta(alpha, beta) || reference Beta) per step, 0 where masked."""
-        alphas, betas, prob_masks = outputs["alphas"].float().cpu(), outputs["betas"].float().cpu(), outputs["prob_masks"].cpu()
-        input_sigmas = F.pad(outputs["sigmas"].float().cpu()[..., :-1], (1, 0), value=1.0)
-        if self.relative:
-            ref_a, ref_b = get_ref_beta(input_sigmas)
-        else:
-            ref_a, ref_b = torch.full_like(alphas, 1.4), torch.full_like(alphas, 11.2)
-        kl = torch.distributions.kl_divergence(torch.distributions.Beta(alphas, betas), torch.distributions.Beta(ref_a, ref_b))
-        return torch.where(prob_masks.bool(), torch.zeros_like(kl), kl)
+        """:875-901 on the device: KL(Beta(alpha, beta) || reference Beta) per step, 0 where masked -> (bs, T)."""
+        from .rloo import shape_rollout
+        return shape_rollout(outputs, None, relative=self.relative)["kl"]
 
     def subset_inputs(self, inputs, micro_batch_inds):
         """:903-914"""

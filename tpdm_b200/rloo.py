@@ -4,12 +4,39 @@ SURVEY.md section 2.1 #6).  rollout (device-side Beta draws) -> reward -> RLOO a
 native TPM backward + flat-buffer all-reduce + fused AdamW."""
 from __future__ import annotations
 
-from typing import Callable, Dict, List
+from typing import Callable, Dict, List, Optional
 
 import numpy as np
 import torch
 
 from .tpm_training import TimePredictorTrainer
+
+
+def shape_rollout(outputs: Dict, last_rewards: Optional[torch.Tensor] = None, *, relative: bool = True, gamma: float = 0.97,
+                  kl_coef: float = 0.0, mean_kl: bool = False, rloo_k: int = 0, ref_steps: int = 28) -> Dict[str, torch.Tensor]:
+    """Device-side reward shaping of one rollout (C ABI ``tpdm_rollout_shaping``): per-step KL to the reference schedule
+    (modeling_sd3_pnt.py:875-901), discounted score (:828-841), ``rlhf_reward = score - kl_coef * kl`` and the RLOO
+    leave-one-out advantage (rloo_trainer.py:447-461).  ``last_rewards`` (B,) is the caller's reward-model score of each
+    final image; ``rloo_k = 0`` skips the advantage."""
+    from . import _lib as L
+    lib = L.load()
+    alphas = outputs["alphas"].float().contiguous()
+    if not alphas.is_cuda:
+        raise RuntimeError("shape_rollout needs the rollout tensors on the CUDA device (there is no CPU path)")
+    dev = alphas.device
+    betas, sigmas = outputs["betas"].float().contiguous(), outputs["sigmas"].float().contiguous()
+    masks = outputs["prob_masks"].to(device=dev, dtype=torch.int32).contiguous()
+    B, T = alphas.shape
+    lr = None if last_rewards is None else last_rewards.to(device=dev, dtype=torch.float32).contiguous()
+    kl = torch.empty(B, T, device=dev)
+    scores, rlhf = torch.empty(B, device=dev), torch.empty(B, device=dev)
+    adv = torch.empty(B, device=dev) if rloo_k else None
+    with torch.cuda.device(dev):
+        L.check(lib.tpdm_rollout_shaping(L.ptr(alphas), L.ptr(betas), L.ptr(sigmas), L.ptr(masks), L.ptr(lr) if lr is not None else None,
+                                         B, T, 1 if relative else 0, ref_steps, gamma, kl_coef, 1 if mean_kl else 0, int(rloo_k),
+                                         L.ptr(kl), L.ptr(scores), L.ptr(rlhf), L.ptr(adv) if adv is not None else None,
+                                         torch.cuda.current_stream().cuda_stream))
+    return dict(kl=kl, scores=scores, rlhf_reward=rlhf, advantages=adv)
 
 
 def rloo_advantages(rlhf_reward: torch.Tensor, rloo_k: int) -> torch.Tensor:
@@ -27,15 +54,9 @@ def rloo_update(wrapper, trainer: TimePredictorTrainer, data: Dict, reward_fn: C
     data = wrapper.rloo_repeat(dict(data), rloo_k)
     outputs = wrapper.sample({**data, "predict": False, "generator": torch.Generator().manual_seed(seed)})
     prob_masks = outputs["prob_masks"]
-    last_reward = reward_fn(outputs["latents"], outputs).float().cpu()
-    scores = []
-    for i in range(prob_masks.shape[0]):       # discounted reward (modeling_sd3_pnt.py:838-841)
-        last = int(outputs["last_valid_indices"][i])
-        scores.append(sum(float(last_reward[i]) * gamma ** (last - j) for j in range(last + 1)) / (last + 1))
-    scores = torch.tensor(scores)
-    kl = wrapper.kl_divergence(outputs) if kl_coef != 0.0 else torch.zeros(scores.shape[0], 1)
-    rlhf_reward = scores + (-kl_coef * kl).sum(1)
-    advantages = rloo_advantages(rlhf_reward, rloo_k).to(agent.device)
+    last_reward = reward_fn(outputs["latents"], outputs).float()
+    shaped = shape_rollout(outputs, last_reward, relative=agent.relative, gamma=gamma, kl_coef=kl_coef, rloo_k=rloo_k)
+    scores, advantages = shaped["scores"].cpu(), shaped["advantages"]
     B = scores.shape[0]
     x = outputs["hidden_states_combineds"].permute(0, 1, 3, 4, 2)     # back to the NHWC storage it is a view of
     logs: List[Dict] = []

@@ -1,7 +1,11 @@
 // tpdm_b200 -- epilogue of the tcgen05 GEMM kernels, shared by the 1-CTA (gemm_tcgen05.cu) and the CTA-pair
-// (gemm2_tcgen05.cu) variants: one warp drains its 32 accumulator rows x BN columns from TMEM in 32-column chunks,
-// transposes each chunk through padded shared memory so that global traffic is row-contiguous 16-byte accesses, and
+// (gemm2_tcgen05.cu) variants: one warp drains its 32 accumulator rows x BN columns from TMEM in 32-column chunks and
 // applies bias / GELU-tanh / x += gate * (acc + bias).
+//   bf16 outputs are stored straight from the accumulator registers (lane = row, 64 contiguous bytes per chunk).  Staging
+//     them through shared memory for fully coalesced stores measured 2-6 % SLOWER on every SD3-medium GEMM shape: the
+//     staging traffic competes with the MMA operand reads and the TMA writes for shared-memory bandwidth.
+//   fp32 outputs (and the fp32 residual read of the gate mode) go through a padded shared-memory transpose so that global
+//     traffic is row-contiguous 16-byte accesses: lane = row with 128-byte rows measured 0.68x (32 lines per request).
 #pragma once
 #include <cuda_bf16.h>
 
@@ -35,12 +39,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
       rows = rows > 32 ? 32 : rows;
       const bool f32_out = G.epi == EPI_BIAS_F32 || G.epi == EPI_GATE_RESIDUAL;
       const bool resid = G.epi == EPI_GATE_RESIDUAL;
-      // Row-contiguous 16-byte global accesses: a lane owns `vec` consecutive columns (8 bf16 / 4 fp32) of one row, so a
-      // warp-wide store covers whole 64 B / 128 B row segments instead of 2 bytes per lane.
-      const int vec = f32_out ? 4 : 8;
-      const int groups = 32 / vec;   // column groups per 32-column chunk
-      const int cg = lane % groups;  // this lane's column group
-      const int r_in = lane / groups;  // this lane's row within a pass (4 rows per pass for bf16, ... 8 passes of 4 for fp32)
+      // fp32 path, after the transpose: a lane owns 4 consecutive columns of one row, so a warp-wide access covers whole
+      // 128-byte row segments of 4 rows
+      const int vec = 4;
+      const int cg = lane % 8;    // this lane's column group within the 32-column chunk
+      const int r_in = lane / 8;  // this lane's row within a pass (8 passes of 4 rows)
       const float* gate_row = resid ? G.gate + static_cast<long long>(batch_idx) * G.gate_stride : nullptr;
       const long long tile_o0 = static_cast<long long>(batch_idx) * G.out_batch_stride + static_cast<long long>(row_base) * G.ldo + n0;
 
@@ -86,17 +89,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
         const int col = n0 + c * 32 + cg * vec;
         const bool col_ok = col < G.N && rows > 0;
         const long long o0 = tile_o0 + c * 32 + cg * vec;
-        float bias[8], gate[4];
+        float bias[4], gate[4];  // fp32 path only (the bf16 path reads its 32 columns' bias as it goes)
         {
-          const float* sb = sbias + (c - c_begin) * 32 + cg * vec;
+          const float* sb = sbias + (c - c_begin) * 32 + cg * 4;
           const float4 b0 = *reinterpret_cast<const float4*>(sb);
           bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
-          if (!f32_out) {
-            const float4 b1 = *reinterpret_cast<const float4*>(sb + 4);
-            bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
-          } else {
-            bias[4] = bias[5] = bias[6] = bias[7] = 0.f;
-          }
           const float4 g4 = *reinterpret_cast<const float4*>(sb + ncol);
           gate[0] = g4.x; gate[1] = g4.y; gate[2] = g4.z; gate[3] = g4.w;
         }
@@ -108,35 +105,39 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
           __syncwarp();
           release_accumulator();
         }
+        if (!f32_out) {
+          if (lane < rows && n0 + c * 32 < G.N) {
+            const bool gelu = G.epi == EPI_BIAS_GELU_BF16;
+            const float* sb = sbias + (c - c_begin) * 32;
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + tile_o0 + c * 32 + static_cast<long long>(lane) * G.ldo;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sb + 8 * q);
+              const float4 b1 = *reinterpret_cast<const float4*>(sb + 8 * q + 4);
+              float y[8] = {__uint_as_float(v[8 * q]) + b0.x,     __uint_as_float(v[8 * q + 1]) + b0.y,
+                            __uint_as_float(v[8 * q + 2]) + b0.z, __uint_as_float(v[8 * q + 3]) + b0.w,
+                            __uint_as_float(v[8 * q + 4]) + b1.x, __uint_as_float(v[8 * q + 5]) + b1.y,
+                            __uint_as_float(v[8 * q + 6]) + b1.z, __uint_as_float(v[8 * q + 7]) + b1.w};
+              if (gelu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) y[e] = gelu_tanh(y[e]);
+              }
+              uint4 w;
+              w.x = pack_bf16x2(y[0], y[1]);
+              w.y = pack_bf16x2(y[2], y[3]);
+              w.z = pack_bf16x2(y[4], y[5]);
+              w.w = pack_bf16x2(y[6], y[7]);
+              if (n0 + c * 32 + 8 * q < G.N) *reinterpret_cast<uint4*>(o + 8 * q) = w;
+            }
+          }
+          return;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           *reinterpret_cast<uint4*>(st + lane * kStagePad + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         __syncwarp();
         if (col_ok) {
-          if (!f32_out) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(G.out) + o0;
-            const bool gelu = G.epi == EPI_BIAS_GELU_BF16;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int r = it * 8 + r_in;
-              if (r < rows) {
-                const float4 x0 = *reinterpret_cast<const float4*>(st + r * kStagePad + cg * 8);
-                const float4 x1 = *reinterpret_cast<const float4*>(st + r * kStagePad + cg * 8 + 4);
-                float y[8] = {x0.x + bias[0], x0.y + bias[1], x0.z + bias[2], x0.w + bias[3],
-                              x1.x + bias[4], x1.y + bias[5], x1.z + bias[6], x1.w + bias[7]};
-                if (gelu) {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) y[e] = gelu_tanh(y[e]);
-                }
-                uint4 w;
-                w.x = pack_bf16x2(y[0], y[1]);
-                w.y = pack_bf16x2(y[2], y[3]);
-                w.z = pack_bf16x2(y[4], y[5]);
-                w.w = pack_bf16x2(y[6], y[7]);
-                *reinterpret_cast<uint4*>(o + static_cast<long long>(r) * G.ldo) = w;
-              }
-            }
-          } else {
+          {
             float* o = reinterpret_cast<float*>(G.out) + o0;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {

@@ -84,6 +84,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture (profiles/, round 1)
+NCU_DRAM_BYTES_PER_LAUNCH = {"gemm_bf16_tcgen05": 141.2e6, "joint_attention_tcgen05": 94.7e6}
+
+
 def mmdit_flops_1024() -> float:
     from oracle.sd3_oracle import mmdit_flops, sd3_medium_config
 
@@ -184,7 +188,10 @@ def run_ours(args, rank, world, local_rank):
     roofline = None
     if dom:
         roofline = dict(bound="tensor", kernel=dom, achieved=kernels[dom]["tflops"], peak=pk["tflops"], unit="TFLOP/s",
-                        frac=kernels[dom]["tflops"] / pk["tflops"], traffic=None, peak_source=pk["source"] + " (sustained bf16)",
+                        frac=kernels[dom]["tflops"] / pk["tflops"], traffic=NCU_DRAM_BYTES_PER_LAUNCH.get(dom),
+                        traffic_source="profiles/r01_gemm2_ncu.txt / r01_attention_ncu.txt: dram__bytes_read+write per launch, "
+                                       "ncu --set full (GEMM: mean of the four per-block shapes)",
+                        peak_source=pk["source"] + " (sustained bf16)",
                         sampled_over="one extra trajectory with per-launch CUDA events, right after the timed region",
                         kernels=kernels)
     steps_per_image = n_denoise / K

@@ -222,6 +222,69 @@ int tpdm_adamw_step(float* params, const float* grads, float* m, float* v, long 
                     void* bf16_copy, long long bf16_n, void* stream);
 
 /* ---- measurement hooks used by bench.py -------------------------------------------------------------------------- */
+/* ----------------------------------------------------------------------------------------------------------------
+ * VAE decode of the final latent.  Replaces, for the decode step only,
+ *   latents = latents / vae.config.scaling_factor + vae.config.shift_factor
+ *   image   = vae.decode(latents, return_dict=False)[0];  image_processor.postprocess(image, "pil")
+ * (/root/reference/src/models/stable_diffusion_3/modeling_sd3_pnt.py:631, 653-655; AutoencoderKL is a diffusers class,
+ * the decoder topology restated here is documented in DESIGN.md section 7).
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct tpdm_vae_config {
+  int latent_channels;        /* 16 for SD3 (<= 64) */
+  int out_channels;           /* 3 (<= 4) */
+  int num_levels;             /* len(block_out_channels), <= 8 */
+  int block_out_channels[8];  /* encoder order, e.g. 128, 256, 512, 512; each a multiple of 64 and of 4*norm_num_groups */
+  int layers_per_block;       /* 2: every up block has layers_per_block + 1 resnets */
+  int norm_num_groups;        /* 32 */
+  float scaling_factor;       /* 1.5305 */
+  float shift_factor;         /* 0.0609 */
+} tpdm_vae_config;
+
+/* 3x3 conv weights: bf16 [Cout][9][Cin] (tap = ky*3 + kx, then input channel); 1x1 / linear weights: bf16 [Cout][Cin];
+ * biases and GroupNorm affine parameters fp32.  All pointers are device pointers borrowed for the lifetime of the ctx. */
+typedef struct tpdm_vae_resnet {
+  const float *norm1_w, *norm1_b;
+  const void* conv1_w;
+  const float* conv1_b;
+  const float *norm2_w, *norm2_b;
+  const void* conv2_w;
+  const float* conv2_b;
+  const void* short_w;        /* conv_shortcut (1x1), NULL when Cin == Cout */
+  const float* short_b;
+} tpdm_vae_resnet;
+
+typedef struct tpdm_vae_weights {
+  const void* conv_in_w;      /* bf16 [C0][9][64]: latent channels zero-padded to 64 */
+  const float* conv_in_b;
+  const tpdm_vae_resnet* resnets; /* mid_block.resnets.0, .1, then up_blocks.{i}.resnets.{j} in order */
+  int n_resnets;              /* = tpdm_vae_num_resnets() */
+  const float *attn_norm_w, *attn_norm_b; /* mid_block.attentions.0.group_norm */
+  const void *attn_q_w, *attn_k_w, *attn_v_w, *attn_o_w;
+  const float *attn_q_b, *attn_k_b, *attn_v_b, *attn_o_b;
+  const void* const* up_conv_w; /* up_blocks.{i}.upsamplers.0.conv, i < num_levels - 1 */
+  const float* const* up_conv_b;
+  int n_upsamplers;
+  const float *norm_out_w, *norm_out_b;   /* conv_norm_out */
+  const void* conv_out_w;     /* bf16 [8][9][C_last]: rows >= out_channels are zero */
+  const float* conv_out_b;    /* fp32 [8] */
+} tpdm_vae_weights;
+
+typedef struct tpdm_vae tpdm_vae;
+int tpdm_vae_create(const tpdm_vae_config* cfg, tpdm_vae** out);
+int tpdm_vae_destroy(tpdm_vae* vae);
+int tpdm_vae_num_resnets(const tpdm_vae* vae);
+int tpdm_vae_set_weights(tpdm_vae* vae, const tpdm_vae_weights* w);
+/* bytes for one decode of a latent_h x latent_w latent (samples of a batch are decoded one after the other) */
+size_t tpdm_vae_workspace_bytes(const tpdm_vae* vae, int latent_h, int latent_w);
+/* latents fp32 NCHW [batch][latent_channels][h][w].  apply_scaling != 0: the input is the sampler's latent and
+ * z = latents / scaling_factor + shift_factor is applied first (modeling_sd3_pnt.py:653); 0: the input is already z (what
+ * AutoencoderKL.decode takes).  Outputs (either may be NULL, not both):
+ * image fp32 NCHW [batch][out_channels][H][W] (what vae.decode returns), rgb uint8 [batch][H][W][out_channels] =
+ * round(clamp(image / 2 + 0.5, 0, 1) * 255) (VaeImageProcessor.postprocess up to the PIL wrapper).  H = h * 2^(levels-1).
+ * workspace: 1 KiB aligned, >= tpdm_vae_workspace_bytes().  Stream-ordered, no host synchronisation. */
+int tpdm_vae_decode(tpdm_vae* vae, const float* latents, int apply_scaling, int batch, int latent_h, int latent_w,
+                    void* workspace, size_t workspace_bytes, float* image, unsigned char* rgb, void* stream);
+
 /* kernels launched by this library in this process since the last reset */
 long long tpdm_launch_count(int reset);
 /* bracket every GEMM (class 0) and attention (class 1) launch with CUDA events on the launching stream until stop;

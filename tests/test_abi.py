@@ -117,3 +117,40 @@ def test_output_container_access_styles():
                                    logprobs=torch.zeros(1), prob_masks=torch.zeros(1).bool())
     assert o.sigmas is o["sigmas"] and o.get("images") == [] and "alphas" in dict(o.items())
     assert o.get("hidden_states_combineds", None) is None
+
+
+def test_vae_module_matches_diffusers_state_dict_layout():
+    """the product AutoencoderKL holds exactly the decoder tensors of the diffusers layout (names shared with the oracle)"""
+    from oracle import vae_oracle as V
+    from tpdm_b200.vae import AutoencoderKL
+
+    for cfg in (V.sd3_vae_config(), V.tiny_vae_config()):
+        ora = V.build_vae(cfg)
+        vae = AutoencoderKL(latent_channels=cfg.latent_channels, block_out_channels=cfg.block_out_channels,
+                            layers_per_block=cfg.layers_per_block, norm_num_groups=cfg.norm_num_groups)
+        a, b = ora.state_dict(), vae.state_dict()
+        assert set(a) == set(b) and all(a[k].shape == b[k].shape for k in a)
+    assert "decoder.up_blocks.2.resnets.0.conv_shortcut.weight" in a or "decoder.up_blocks.1.resnets.0.conv_shortcut.weight" in a
+    assert vae.upscale == 2 and AutoencoderKL().upscale == 8
+
+
+def test_vae_has_no_cpu_path():
+    import pytest
+    import torch
+    from tpdm_b200.vae import AutoencoderKL
+
+    vae = AutoencoderKL(block_out_channels=(64, 128), layers_per_block=1, norm_num_groups=16)
+    with pytest.raises((RuntimeError, ValueError, OSError)):
+        vae.decode(torch.zeros(1, 16, 8, 8))
+
+
+def test_vae_oracle_shapes_and_flops():
+    import torch
+    from oracle import vae_oracle as V
+
+    t = V.build_vae(V.tiny_vae_config())
+    img = t.decode_latents(torch.randn(1, 16, 8, 8, generator=torch.Generator().manual_seed(0)))
+    assert img.shape == (1, 3, 16, 16) and bool(torch.isfinite(img).all())
+    u8 = V.postprocess_uint8(img)
+    assert u8.shape == (1, 16, 16, 3) and u8.dtype == torch.uint8
+    assert abs(V.decode_flops(V.sd3_vae_config(), 128, 128) / 1e12 - 10.47) < 0.05

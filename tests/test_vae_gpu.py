@@ -1,0 +1,107 @@
+"""GPU parity of the native VAE decode against the fp32 oracle restatement (oracle/vae_oracle.py,
+parity unpinned: diffusers is absent).  bf16 tensor-core convolutions vs fp32: image rel-L2 <= 3e-2 (the final-latent
+tolerance of the path), uint8 pixels within 4 levels (mean < 0.5) of the oracle's post-processing."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 3e-2
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _pair(cfg, seed=4321):
+    from oracle import vae_oracle as V
+    from tpdm_b200.vae import AutoencoderKL
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    ora = V.build_vae(cfg, seed).cuda()
+    vae = AutoencoderKL(latent_channels=cfg.latent_channels, out_channels=cfg.out_channels, block_out_channels=cfg.block_out_channels,
+                        layers_per_block=cfg.layers_per_block, norm_num_groups=cfg.norm_num_groups, scaling_factor=cfg.scaling_factor,
+                        shift_factor=cfg.shift_factor, device="cuda", dtype=torch.float32)
+    vae.load_state_dict(ora.state_dict())
+    return ora, vae
+
+
+@pytest.mark.parametrize("h,w,batch", [(8, 8, 1), (16, 32, 2), (64, 64, 1)])
+def test_tiny_vae_decode_matches_oracle(h, w, batch):
+    from oracle import vae_oracle as V
+
+    ora, vae = _pair(V.tiny_vae_config())
+    g = torch.Generator(device="cuda").manual_seed(h * 100 + w)
+    lat = torch.randn(batch, 16, h, w, device="cuda", generator=g)
+    ref = ora.decode_latents(lat)
+    img = vae.decode_latents(lat, "pt")
+    assert img.shape == ref.shape == (batch, 3, 2 * h, 2 * w)
+    assert rel(img, ref) < IMG_TOL
+    # AutoencoderKL.decode takes the un-scaled z
+    z = lat / vae.config.scaling_factor + vae.config.shift_factor
+    assert rel(vae.decode(z, return_dict=False)[0], ref) < IMG_TOL
+    rgb = vae.decode_latents(lat, "uint8")
+    want = V.postprocess_uint8(ref)
+    assert rgb.shape == want.shape and rgb.dtype == torch.uint8
+    diff = (rgb.int() - want.int()).abs()
+    assert int(diff.max()) <= 4 and float(diff.float().mean()) < 0.5      # bf16 activations: a few grey levels at most
+
+
+def test_sd3_vae_decode_256_matches_oracle():
+    """Full SD3 decoder topology (128/256/512/512, 3 resnets per level, 512-wide single-head attention) on a 32x32 latent."""
+    from oracle import vae_oracle as V
+
+    ora, vae = _pair(V.sd3_vae_config())
+    g = torch.Generator(device="cuda").manual_seed(9)
+    lat = torch.randn(1, 16, 32, 32, device="cuda", generator=g)
+    ref = ora.decode_latents(lat)
+    img = vae.decode_latents(lat, "pt")
+    assert img.shape == (1, 3, 256, 256)
+    assert rel(img, ref) < IMG_TOL
+    pil = vae.decode_latents(lat, "pil")
+    assert len(pil) == 1 and pil[0].size == (256, 256)
+
+
+def test_sd3_vae_decode_1024_properties():
+    """Full size (128x128 latent -> 1024^2, 16 384-token attention): finite, deterministic, and equal to the decode of the
+    same latent inside a batch of two (samples are independent)."""
+    from oracle import vae_oracle as V
+
+    _, vae = _pair(V.sd3_vae_config())
+    g = torch.Generator(device="cuda").manual_seed(10)
+    lat = torch.randn(2, 16, 128, 128, device="cuda", generator=g)
+    a = vae.decode_latents(lat[:1], "pt")
+    b = vae.decode_latents(lat, "pt")
+    assert a.shape == (1, 3, 1024, 1024) and bool(torch.isfinite(b).all())
+    assert torch.equal(a[0], b[0])
+    assert not torch.equal(b[0], b[1])
+
+
+def test_pipeline_returns_images_when_vae_attached():
+    """modeling_sd3_pnt.py:645-655: with a VAE the pipeline output carries one [PIL image] list per prompt, decoded from
+    the last valid latent of each trajectory."""
+    from oracle import sd3_oracle as O
+    from oracle import vae_oracle as V
+    from tpdm_b200.modeling_sd3_pnt import SD3PredictNextTimeStepModel
+
+    vc = V.tiny_vae_config()
+    tiny = dict(sample_size=32, patch_size=2, in_channels=16, num_layers=2, attention_head_dim=96, num_attention_heads=4,
+                joint_attention_dim=4096, caption_projection_dim=384, pooled_projection_dim=2048, out_channels=16, pos_embed_max_size=96)
+    torch.manual_seed(7)
+    model = SD3PredictNextTimeStepModel(transformer_config=tiny, torch_dtype=torch.bfloat16, device="cuda",
+                                        vae_config=dict(block_out_channels=vc.block_out_channels, layers_per_block=vc.layers_per_block,
+                                                        norm_num_groups=vc.norm_num_groups))
+    assert model.vae_scale_factor == 2
+    g = torch.Generator().manual_seed(0)
+    mk = lambda *s: torch.randn(*s, generator=g).cuda()
+    kw = dict(prompt_embeds=mk(2, 333, 4096), negative_prompt_embeds=mk(2, 333, 4096), pooled_prompt_embeds=mk(2, 2048),
+              negative_pooled_prompt_embeds=mk(2, 2048), latents=mk(2, 16, 32, 32), max_inference_steps=4, predict=True)
+    out = model(**kw)
+    assert len(out.images) == 2 and out.images[0][0].size == (64, 64)
+    out_pt = model(**kw, output_type="pt")
+    ora = V.build_vae(vc).cuda()
+    ora.load_state_dict({k: v.float() for k, v in model.vae.state_dict().items()})
+    ref = ora.decode_latents(out_pt.latents.float())
+    assert rel(torch.cat(out_pt.images), ref) < IMG_TOL

@@ -39,6 +39,27 @@ class TpdmWeights(C.Structure):
     _fields_ = [(n, vp) for n in GLOBAL_FIELDS_A] + [("blocks", C.POINTER(TpdmBlockWeights))] + [(n, vp) for n in GLOBAL_FIELDS_B]
 
 
+class TpdmVaeConfig(C.Structure):
+    _fields_ = [("latent_channels", C.c_int32), ("out_channels", C.c_int32), ("num_levels", C.c_int32),
+                ("block_out_channels", C.c_int32 * 8), ("layers_per_block", C.c_int32), ("norm_num_groups", C.c_int32),
+                ("scaling_factor", C.c_float), ("shift_factor", C.c_float)]
+
+
+VAE_RESNET_FIELDS = ("norm1_w", "norm1_b", "conv1_w", "conv1_b", "norm2_w", "norm2_b", "conv2_w", "conv2_b", "short_w", "short_b")
+
+
+class TpdmVaeResnet(C.Structure):
+    _fields_ = [(n, vp) for n in VAE_RESNET_FIELDS]
+
+
+class TpdmVaeWeights(C.Structure):
+    _fields_ = ([("conv_in_w", vp), ("conv_in_b", vp), ("resnets", C.POINTER(TpdmVaeResnet)), ("n_resnets", C.c_int32)] +
+                [(n, vp) for n in ("attn_norm_w", "attn_norm_b", "attn_q_w", "attn_k_w", "attn_v_w", "attn_o_w",
+                                   "attn_q_b", "attn_k_b", "attn_v_b", "attn_o_b")] +
+                [("up_conv_w", C.POINTER(vp)), ("up_conv_b", C.POINTER(vp)), ("n_upsamplers", C.c_int32)] +
+                [(n, vp) for n in ("norm_out_w", "norm_out_b", "conv_out_w", "conv_out_b")])
+
+
 class TpdmSampleState(C.Structure):
     _fields_ = [(n, vp) for n in ("latents", "velocity", "sigma_hist", "alphas", "betas", "logprobs", "prob_masks",
                                   "all_done", "tembs", "tpm_input", "history_latents")]
@@ -66,6 +87,12 @@ EXPORTS = {
     "tpdm_tpm_trainer_bind": (C.c_int, [vp, vp, vp, vp]),
     "tpdm_tpm_train_forward": (C.c_int, [vp, vp, vp, C.c_int, vp, vp]),
     "tpdm_tpm_train_backward": (C.c_int, [vp, vp, vp]),
+    "tpdm_vae_create": (C.c_int, [C.POINTER(TpdmVaeConfig), C.POINTER(vp)]),
+    "tpdm_vae_destroy": (C.c_int, [vp]),
+    "tpdm_vae_num_resnets": (C.c_int, [vp]),
+    "tpdm_vae_set_weights": (C.c_int, [vp, C.POINTER(TpdmVaeWeights)]),
+    "tpdm_vae_workspace_bytes": (C.c_size_t, [vp, C.c_int, C.c_int]),
+    "tpdm_vae_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp]),
     "tpdm_rollout_shaping": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                        vp, vp, vp, vp, vp]),
     "tpdm_ppo_clip_loss": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]),

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtpdm_b200.so")
-SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "attention_tcgen05.cu", "kernels.cu", "tpm_train.cu", "api.cu"]
+SOURCES = ["runtime.cu", "gemm_tcgen05.cu", "gemm2_tcgen05.cu", "attention_tcgen05.cu", "kernels.cu", "tpm_train.cu", "vae.cu", "api.cu"]
 HEADERS = ["common.cuh", "gemm_epilogue.cuh", "host.h", "kernels.h", os.path.join("..", "..", "include", "tpdm_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",

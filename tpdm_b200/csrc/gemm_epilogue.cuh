@@ -38,6 +38,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
       int rows = G.rows_per_batch - row_base;
       rows = rows > 32 ? 32 : rows;
       const bool f32_out = G.epi == EPI_BIAS_F32 || G.epi == EPI_GATE_RESIDUAL;
+      const bool add_bf16 = G.epi == EPI_BIAS_ADD_BF16;
       const bool resid = G.epi == EPI_GATE_RESIDUAL;
       // fp32 path, after the transpose: a lane owns 4 consecutive columns of one row, so a warp-wide access covers whole
       // 128-byte row segments of 4 rows
@@ -121,6 +122,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmOp& G, int batch_id
               if (gelu) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) y[e] = gelu_tanh(y[e]);
+              }
+              if (add_bf16 && n0 + c * 32 + 8 * q < G.N) {
+                const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(G.res) + (o - reinterpret_cast<__nv_bfloat16*>(G.out)) + 8 * q);
+                y[0] += __uint_as_float(a.x << 16); y[1] += __uint_as_float(a.x & 0xffff0000u);
+                y[2] += __uint_as_float(a.y << 16); y[3] += __uint_as_float(a.y & 0xffff0000u);
+                y[4] += __uint_as_float(a.z << 16); y[5] += __uint_as_float(a.z & 0xffff0000u);
+                y[6] += __uint_as_float(a.w << 16); y[7] += __uint_as_float(a.w & 0xffff0000u);
               }
               uint4 w;
               w.x = pack_bf16x2(y[0], y[1]);

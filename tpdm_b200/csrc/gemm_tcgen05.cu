@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
           if (G.conv) {
             const int tap = kb / G.kb_per_tap;
             const int c0 = (kb - tap * G.kb_per_tap) * BK;
-            tma_load_4d(sA, &G.tmA, &full_bar[stage], c0, tap % 3 - 1, tc.mt * G.conv_by + tap / 3 - 1, tc.b);
+            const int yt = tc.mt / G.conv_xt, xt = tc.mt - yt * G.conv_xt;
+            tma_load_4d(sA, &G.tmA, &full_bar[stage], c0, xt * G.conv_bx + tap % 3 - 1, yt * G.conv_by + tap / 3 - 1, tc.b);
           } else {
             tma_load_3d(sA, &G.tmA, &full_bar[stage], kb * BK, tc.mt * BM, tc.b);
           }
@@ -299,12 +300,39 @@ int gemm_op_init_conv3x3(GemmOp* op, const void* X, int batch, int g, int C, con
   op->tiles_m_per_batch = (g * g + BM - 1) / BM;
   op->conv = 1;
   op->conv_by = BM / g;
+  op->conv_bx = g;
+  op->conv_xt = 1;
   op->kb_per_tap = C / BK;
   uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(g), static_cast<uint64_t>(g), static_cast<uint64_t>(batch)};
   uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * g * 2, static_cast<uint64_t>(C) * g * g * 2};
   uint32_t box[4] = {BK, static_cast<uint32_t>(g), static_cast<uint32_t>(BM / g), 1};
   TPDM_TRY(encode_tmap_bf16(&op->tmA, X, 4, dims, strides, box));
   return finish_op(op, W, N, 9 * C, epi, out, static_cast<long long>(g) * g * ldo, ldo, bias, nullptr, 0);
+}
+
+int gemm_op_init_conv3x3_hw(GemmOp* op, const void* X, int batch, int H, int Wd, int C, const void* W, int N, int epi, void* out,
+                            int ldo, const float* bias, const void* res) {
+  *op = GemmOp{};
+  const int bx = Wd < BM ? Wd : BM;
+  TPDM_CHECK(H > 0 && Wd >= 8 && (Wd >= BM ? Wd % BM == 0 : (Wd & (Wd - 1)) == 0), TPDM_ERR_SHAPE,
+             "conv3x3: image width %d must be a multiple of 128 or a power of two in [8,128)", Wd);
+  TPDM_CHECK(C % BK == 0, TPDM_ERR_SHAPE, "conv3x3: C=%d must be a multiple of 64", C);
+  TPDM_CHECK(epi != EPI_BIAS_ADD_BF16 || (res != nullptr && (reinterpret_cast<uintptr_t>(res) & 15) == 0), TPDM_ERR_ARG,
+             "conv3x3: the add epilogue needs a 16-byte aligned addend");
+  op->rows_per_batch = H * Wd;
+  op->batch = batch;
+  op->tiles_m_per_batch = (H * Wd + BM - 1) / BM;
+  op->conv = 1;
+  op->conv_bx = bx;
+  op->conv_by = BM / bx;
+  op->conv_xt = Wd / bx;
+  op->kb_per_tap = C / BK;
+  op->res = res;
+  uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(Wd), static_cast<uint64_t>(H), static_cast<uint64_t>(batch)};
+  uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * Wd * 2, static_cast<uint64_t>(C) * Wd * H * 2};
+  uint32_t box[4] = {BK, static_cast<uint32_t>(bx), static_cast<uint32_t>(BM / bx), 1};
+  TPDM_TRY(encode_tmap_bf16(&op->tmA, X, 4, dims, strides, box));
+  return finish_op(op, W, N, 9 * C, epi, out, static_cast<long long>(H) * Wd * ldo, ldo, bias, nullptr, 0);
 }
 
 int gemm_op_init_conv3x3_wgrad(GemmOp* op, const void* dYt, const void* Xnchw, int samples, int g, int C, int M, float* dW) {

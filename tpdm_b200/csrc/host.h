@@ -75,6 +75,7 @@ enum GemmEpilogue : int {
   EPI_BIAS_F32 = 1,        // out(f32)  = acc + bias
   EPI_BIAS_GELU_BF16 = 2,  // out(bf16) = gelu_tanh(acc + bias)
   EPI_GATE_RESIDUAL = 3,   // out(f32) += gate[b, n] * (acc + bias)
+  EPI_BIAS_ADD_BF16 = 4,   // out(bf16) = acc + bias + res(bf16)   (VAE resnet / attention skip connections)
 };
 
 struct alignas(64) GemmOp {
@@ -84,6 +85,8 @@ struct alignas(64) GemmOp {
   int rows_per_batch, batch, N, K;
   int tiles_m_per_batch, tiles_n, num_tiles, block_n;
   int conv, conv_by, kb_per_tap, epi;  // conv: 0 plain, 1 conv3x3 forward, 2 conv3x3 weight gradient
+  int conv_bx = 0, conv_xt = 1;        // conv 1: pixels per tile row segment, tile segments per image row
+  const void* res = nullptr;           // EPI_BIAS_ADD_BF16: bf16 addend, indexed exactly like `out` (may alias it)
   int wg_px, wg_bpr, wg_ctiles, wg_pad;
   void* out;
   long long out_batch_stride;  // elements between batches of the output
@@ -100,6 +103,10 @@ int gemm_op_init(GemmOp* op, const void* A, long long a_row_stride, long long a_
 // implicit-GEMM 3x3 / pad 1 / stride 1 convolution over NHWC bf16 X[b][g][g][C]; W packed [N][9*C] (tap-major, tap=ky*3+kx).
 int gemm_op_init_conv3x3(GemmOp* op, const void* X, int batch, int g, int C, const void* W, int N, int epi, void* out,
                          int ldo, const float* bias);
+// same over a rectangular image X[b][H][Wd][C]: a 128-pixel M tile is a 128-wide segment of one row (Wd >= 128, Wd % 128 == 0)
+// or 128 / Wd whole rows (Wd a power of two < 128); `res` as in GemmOp
+int gemm_op_init_conv3x3_hw(GemmOp* op, const void* X, int batch, int H, int Wd, int C, const void* W, int N, int epi, void* out,
+                            int ldo, const float* bias, const void* res);
 // conv3x3 (pad 1, stride 1) weight gradient as a GEMM: dW[m][tap][c] = sum_{sample,pix} dYt[sample][m][pix] * X[sample][c][pix+tap]
 // dYt bf16 [samples][M][g*g]; X bf16 as THREE x-shifted NCHW copies [samples][3][C][g][g], copy k holding X[.., x + k - 1]
 // (zero outside), so no TMA load needs an unaligned innermost coordinate; dW fp32 [M][9][C] (overwritten)

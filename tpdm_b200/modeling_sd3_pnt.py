@@ -114,6 +114,7 @@ class SD3PredictNextTimeStepModel(nn.Module):
         prediction_type="alpha_beta",
         transformer_config: Optional[dict] = None,
         device=None,
+        vae_config: Optional[dict] = None,
     ):
         """Reference kwargs (modeling_sd3_pnt.py:130-140) plus ``transformer_config`` / ``device`` for offline random-init
         construction (the reference only has ``from_pretrained``)."""
@@ -132,7 +133,25 @@ class SD3PredictNextTimeStepModel(nn.Module):
                 if k in raw:
                     cfg[k] = raw[k]
             weights_file = os.path.join(pretrained_model_name_or_path, "transformer", "diffusion_pytorch_model.safetensors")
-        self.vae = None            # out of scope; attach a module with .decode/.config to get images
+        # VAE: built from `vae_config` or <path>/vae/config.json; otherwise None and the caller may attach
+        # any module with .decode / .config.  Only the decoder exists (tpdm_b200/vae.py); images stay off when vae is None.
+        self.vae = None
+        vae_weights = None
+        if vae_config is None and pretrained_model_name_or_path is not None:
+            vcfg_path = os.path.join(pretrained_model_name_or_path, "vae", "config.json")
+            if os.path.isfile(vcfg_path):
+                rawv = json.load(open(vcfg_path))
+                vae_config = {k: rawv[k] for k in ("latent_channels", "out_channels", "block_out_channels", "layers_per_block",
+                                                   "norm_num_groups", "scaling_factor", "shift_factor") if k in rawv}
+                vae_weights = os.path.join(pretrained_model_name_or_path, "vae", "diffusion_pytorch_model.safetensors")
+        if vae_config is not None:
+            from .vae import AutoencoderKL
+
+            self.vae = AutoencoderKL(**vae_config, device=device, dtype=torch_dtype)
+            if vae_weights is not None and os.path.isfile(vae_weights):
+                from safetensors.torch import load_file
+
+                self.vae.load_state_dict(load_file(vae_weights), strict=False)
         self.transformer = CustomSD3Transformer2DModel(**cfg, device=device, dtype=torch_dtype)
         if weights_file is not None and os.path.isfile(weights_file):
             from safetensors.torch import load_file
@@ -143,7 +162,7 @@ class SD3PredictNextTimeStepModel(nn.Module):
             init_alpha=init_alpha, init_beta=init_beta, device=device, dtype=torch_dtype)
         self.scheduler = CustomFlowMatchEulerDiscreteScheduler()
         self.pre_process = pre_process
-        self.vae_scale_factor = 8
+        self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1) if self.vae is not None else 8   # :181-183
         self.tokenizer_max_length = 77
         self.default_sample_size = self.transformer.config.sample_size
         self.patch_size = self.transformer.config.patch_size
@@ -215,8 +234,10 @@ class SD3PredictNextTimeStepModel(nn.Module):
         predict: bool = False,
         ratios: Optional[torch.Tensor] = None,
         return_velocities: bool = False,
+        output_type: str = "pil",
     ) -> CustomDiffusionModelOutput:
-        """Reference signature (modeling_sd3_pnt.py:447-463) + two additions:
+        """Reference signature (modeling_sd3_pnt.py:447-463) + additions: ``output_type`` ("pil" as the reference's
+        image_processor.postprocess, "uint8" device tensors (1, H, W, 3), "pt" fp32 (1, 3, H, W)) for the images and:
         ``ratios`` (B, max_inference_steps): Beta draws to inject when predict=False so that two implementations follow
         one trajectory; when omitted the draws are made on the device (the reference calls ``beta_dist.sample()``, :569),
         seeded from ``generator``.  ``return_velocities`` records the per-step CFG velocity (parity tests)."""
@@ -255,7 +276,10 @@ class SD3PredictNextTimeStepModel(nn.Module):
             finals.append(hist[i, lv])
         finals = torch.stack(finals).to(out_dtype)
         images = []
-        if self.vae is not None and hasattr(self.vae, "decode"):                   # :645-655 (VAE is caller-supplied)
+        if self.vae is not None and hasattr(self.vae, "decode_latents"):          # :645-655 on the native decoder, one call
+            decoded = self.vae.decode_latents(finals, output_type)
+            images = [[im] for im in decoded] if output_type == "pil" else [decoded[i:i + 1] for i in range(batch_size)]
+        elif self.vae is not None and hasattr(self.vae, "decode"):                 # a caller-supplied module
             for i in range(batch_size):
                 lat = (finals[i] / self.vae.config.scaling_factor) + self.vae.config.shift_factor
                 images.append(self.vae.decode(lat.unsqueeze(0).to(self.vae.dtype), return_dict=False)[0].detach())

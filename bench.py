@@ -176,6 +176,27 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
 
+    # ---- outside every timed region: the step after the path, VAE decode of one final latent to 1024^2 uint8 pixels
+    # (SURVEY 8(f) rank 1), so that a pixels-out rate can be derived; random-init SD3 decoder (49.5 M parameters)
+    vae_ms = None
+    try:
+        from tpdm_b200.vae import AutoencoderKL
+
+        vae = AutoencoderKL(device=dev, dtype=torch.float32)
+        lat = out.latents.float()
+        vae.decode_latents(lat, "uint8")
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        v0.record()
+        for _ in range(3):
+            vae.decode_latents(lat, "uint8")
+        v1.record()
+        torch.cuda.synchronize()
+        vae_ms = v0.elapsed_time(v1) / 3
+        del vae
+    except Exception as e:  # the decode is not part of the metric: report, do not fail the bench
+        vae_ms = f"failed: {e}"
+
     if rank != 0:
         return None
     pk = peaks()
@@ -208,6 +229,12 @@ def run_ours(args, rank, world, local_rank):
         "mmdit_step": {"ms_per_denoise_step": ms_value / n_denoise, "tflops": step_tflops, "frac_of_sustained_peak": step_tflops / pk["tflops"],
                        "algorithmic_tflop_per_step": mmdit_flops_1024() / 1e12},
     }
+    if isinstance(vae_ms, float):
+        line["vae_decode"] = {"ms_per_image": vae_ms, "tflops": 10.472e12 / vae_ms / 1e9, "in_timed_region": False,
+                              "images_per_s_with_decode": world / (ms_value / K / 1e3 + vae_ms / 1e3),
+                              "note": "SD3 VAE decoder, 128x128 latent -> 1024^2 uint8, measured after the timed regions"}
+    else:
+        line["vae_decode"] = {"error": str(vae_ms)}
     if world == 1:
         line["cpu_baseline"] = cpu_baseline(steps_per_image)
     return line

@@ -128,6 +128,24 @@ if __name__ == "__main__":
         gemm_case(2, 4429, 6144, 1536, 2)
         gemm_case(2, 4429, 1536, 6144, 3)
         gemm_case(2, 4429, 1536, 1536, 3)
+    if which == "vae":   # SD3 VAE decode of a 128x128 latent (1024^2 image): time + GEMM-class share
+        import ctypes as C
+        from tpdm_b200.vae import AutoencoderKL
+        torch.manual_seed(4321)
+        vae = AutoencoderKL(device="cuda", dtype=torch.float32)
+        side = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+        lat = torch.randn(1, 16, side, side, device="cuda")
+        fn = lambda: vae.decode_latents(lat, "uint8")
+        fn()
+        ms = timeit(fn, 5)
+        L.check(lib.tpdm_profile_start(4096))
+        fn()
+        torch.cuda.synchronize()
+        pms, pfl, pct = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
+        L.check(lib.tpdm_profile_stop(pms, pfl, pct, 2))
+        flops = 10.472e12 * (side / 128) ** 2 if side == 128 else float("nan")
+        print(f"vae decode {side*8}^2: {ms:.2f} ms  ({flops/ms/1e9:.0f} TFLOP/s algorithmic); GEMM-class kernels {pms[0]:.2f} ms over {pct[0]} launches "
+              f"({pfl[0]/pms[0]/1e9:.0f} TFLOP/s), everything else {ms - pms[0]:.2f} ms; workspace {vae._workspace.numel()/2**30:.2f} GiB", flush=True)
     if which == "ln":
         for (batch, rows) in ((2, 4096), (2, 333)):
             D = 1536

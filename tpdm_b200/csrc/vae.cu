@@ -27,6 +27,12 @@ constexpr int kCinPad = 64;   // latent channels are zero-padded to one 64-wide 
 constexpr int kOutPad = 8;    // conv_out produces 8 fp32 columns per pixel (3 used)
 constexpr int kAttnChunk = 16384;  // query rows per attention chunk (bounds the S / P workspace)
 
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 // latents NCHW fp32 [Cl][h][w] (one sample) -> z = latents / scaling + shift, NHWC bf16 [h][w][64]
 __global__ void vae_prep_latent_kernel(const float* __restrict__ lat, bf16* __restrict__ z, int Cl, int hw, float inv_scale, float shift) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -42,15 +48,25 @@ __global__ void __launch_bounds__(256) vae_gn_stats_kernel(const bf16* __restric
   const int slot = threadIdx.x % slots;         // blockDim.x is a multiple of slots (checked by the launcher)
   const int ppb = blockDim.x / slots;           // pixels per block-iteration
   float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
-  for (long long p = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / slots; p < P; p += static_cast<long long>(gridDim.x) * ppb) {
-    const uint4 v = *reinterpret_cast<const uint4*>(x + p * C + slot * 8);
-    const float a0 = __uint_as_float(v.x << 16), a1 = __uint_as_float(v.x & 0xffff0000u), a2 = __uint_as_float(v.y << 16),
-                a3 = __uint_as_float(v.y & 0xffff0000u), b0 = __uint_as_float(v.z << 16), b1 = __uint_as_float(v.z & 0xffff0000u),
-                b2 = __uint_as_float(v.w << 16), b3 = __uint_as_float(v.w & 0xffff0000u);
-    s0 += (a0 + a1) + (a2 + a3);
-    q0 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-    s1 += (b0 + b1) + (b2 + b3);
-    q1 += (b0 * b0 + b1 * b1) + (b2 * b2 + b3 * b3);
+  const long long pstride = static_cast<long long>(gridDim.x) * ppb;
+  for (long long p0 = static_cast<long long>(blockIdx.x) * ppb + threadIdx.x / slots; p0 < P; p0 += 4 * pstride) {
+    uint4 vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long p = p0 + u * pstride;
+      vv[u] = p < P ? ldg_nc_u4(x + p * C + slot * 8) : make_uint4(0u, 0u, 0u, 0u);   // zeros add nothing to either sum
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint4 v = vv[u];
+      const float a0 = __uint_as_float(v.x << 16), a1 = __uint_as_float(v.x & 0xffff0000u), a2 = __uint_as_float(v.y << 16),
+                  a3 = __uint_as_float(v.y & 0xffff0000u), b0 = __uint_as_float(v.z << 16), b1 = __uint_as_float(v.z & 0xffff0000u),
+                  b2 = __uint_as_float(v.w << 16), b3 = __uint_as_float(v.w & 0xffff0000u);
+      s0 += (a0 + a1) + (a2 + a3);
+      q0 += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      s1 += (b0 + b1) + (b2 + b3);
+      q1 += (b0 * b0 + b1 * b1) + (b2 * b2 + b3 * b3);
+    }
   }
   __shared__ float red[256 * 4];
   red[threadIdx.x * 4 + 0] = s0;
@@ -69,7 +85,7 @@ __global__ void __launch_bounds__(256) vae_gn_stats_kernel(const bf16* __restric
   }
 }
 
-__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }  // MUFU.EX2 + MUFU.RCP: the IEEE division made the apply pass compute-bound
 
 // y = (x - mean_g) * rstd_g * gamma[c] + beta[c], optional SiLU; x, y NHWC bf16 [P][C]; groups of C / G channels (>= 4)
 __global__ void __launch_bounds__(256) vae_gn_apply_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, long long P, int C, int G,
@@ -92,28 +108,40 @@ __global__ void __launch_bounds__(256) vae_gn_apply_kernel(const bf16* __restric
   __syncthreads();
   const int slots = C / 8;
   const long long total = P * slots;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int slot = static_cast<int>(i % slots);
-    const int c0 = slot * 8;
-    const uint4 v = *reinterpret_cast<const uint4*>(x + i * 8);
-    float f[8] = {__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u),
-                  __uint_as_float(v.z << 16), __uint_as_float(v.z & 0xffff0000u), __uint_as_float(v.w << 16), __uint_as_float(v.w & 0xffff0000u)};
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
-    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const int ga = c0 / cpg, gb = (c0 + 4) / cpg;  // the two 4-channel units of this slot may sit in different groups
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  // four 16-byte loads in flight per thread (a single load per iteration reached 43 % of the HBM rate)
+  for (long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 v[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int g = e < 4 ? ga : gb;
-      float r = (f[e] - mean_s[g]) * rstd_s[g] * gm[e] + bt[e];
-      f[e] = act ? silu(r) : r;
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total) v[u] = ldg_nc_u4(x + i * 8);
     }
-    uint4 w;
-    w.x = pack_bf16x2(f[0], f[1]);
-    w.y = pack_bf16x2(f[2], f[3]);
-    w.z = pack_bf16x2(f[4], f[5]);
-    w.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(y + i * 8) = w;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= total) break;
+      const int c0 = static_cast<int>(i % slots) * 8;
+      float f[8] = {__uint_as_float(v[u].x << 16), __uint_as_float(v[u].x & 0xffff0000u), __uint_as_float(v[u].y << 16),
+                    __uint_as_float(v[u].y & 0xffff0000u), __uint_as_float(v[u].z << 16), __uint_as_float(v[u].z & 0xffff0000u),
+                    __uint_as_float(v[u].w << 16), __uint_as_float(v[u].w & 0xffff0000u)};
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + c0), g1 = *reinterpret_cast<const float4*>(gamma + c0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + c0), b1 = *reinterpret_cast<const float4*>(beta + c0 + 4);
+      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const int ga = c0 / cpg, gb = (c0 + 4) / cpg;  // the two 4-channel units of this slot may sit in different groups
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int g = e < 4 ? ga : gb;
+        const float r = (f[e] - mean_s[g]) * rstd_s[g] * gm[e] + bt[e];
+        f[e] = act ? silu(r) : r;
+      }
+      uint4 w;
+      w.x = pack_bf16x2(f[0], f[1]);
+      w.y = pack_bf16x2(f[2], f[3]);
+      w.z = pack_bf16x2(f[4], f[5]);
+      w.w = pack_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(y + i * 8) = w;
+    }
   }
 }
 
@@ -265,9 +293,9 @@ int gn(const bf16* x, bf16* y, long long P, int C, int G, const float* gamma, co
              "vae group norm: unsupported channels %d / groups %d", C, G);
   TPDM_CUDA_OK(cudaMemsetAsync(stats, 0, static_cast<size_t>(C / 4) * 2 * sizeof(double), s));
   const int ppb = 256 / (C / 8);
-  vae_gn_stats_kernel<<<blocks_for(P, ppb * 8, 4 * num_sms()), 256, 0, s>>>(x, P, C, stats);
+  vae_gn_stats_kernel<<<blocks_for(P, ppb * 4, 8 * num_sms()), 256, 0, s>>>(x, P, C, stats);
   count_launch();
-  vae_gn_apply_kernel<<<blocks_for(P * (C / 8), 256 * 4, 8 * num_sms()), 256, 0, s>>>(x, y, P, C, G, stats, gamma, beta, 1e-6f, act);
+  vae_gn_apply_kernel<<<blocks_for(P * (C / 8), 256 * 4, 16 * num_sms()), 256, 0, s>>>(x, y, P, C, G, stats, gamma, beta, 1e-6f, act);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

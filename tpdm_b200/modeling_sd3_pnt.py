@@ -199,10 +199,27 @@ class SD3PredictNextTimeStepModel(nn.Module):
         self._engine_key = (key_t, key_p)
         return self._engine
 
-    def encode_prompt(self, *args, **kwargs):
-        raise NotImplementedError(
-            "text encoders (CLIP-L, CLIP-G, T5-XXL) are outside the tpdm_b200 hot path: pass prompt_embeds, "
-            "negative_prompt_embeds, pooled_prompt_embeds and negative_pooled_prompt_embeds (SURVEY.md section 8f)")
+    def encode_prompt(self, prompt=None, negative_prompt=None, num_images_per_prompt: int = 1, device=None, **unused):
+        """Reference signature (modeling_sd3_pnt.py:296-380) for the ``pre_process`` hand-over: the three text towers are
+        outside this package, so prompts are resolved through ``self.embedding_cache`` (tpdm_b200/embed_cache.py)."""
+        cache = getattr(self, "embedding_cache", None)
+        if cache is None:
+            raise NotImplementedError(
+                "text encoders (CLIP-L, CLIP-G, T5-XXL) are outside the tpdm_b200 hot path: pass prompt_embeds, "
+                "negative_prompt_embeds, pooled_prompt_embeds and negative_pooled_prompt_embeds, or attach a "
+                "PromptEmbeddingCache as model.embedding_cache (SURVEY.md section 8f)")
+        if prompt is None:
+            raise ValueError("prompt or prompt_embeds must be given")
+        prompts = [prompt] if isinstance(prompt, str) else list(prompt)
+        negs = negative_prompt if negative_prompt is not None else ""
+        negs = [negs] * len(prompts) if isinstance(negs, str) else list(negs)
+        if len(negs) != len(prompts):
+            raise ValueError(f"negative_prompt has batch size {len(negs)}, prompt has {len(prompts)}")   # :367-372
+        device = device or self.device
+        pe, pp = cache.get_batch(prompts, device=device)
+        ne, np_ = cache.get_batch(negs, device=device)
+        rep = lambda t: t.repeat_interleave(num_images_per_prompt, dim=0) if num_images_per_prompt > 1 else t
+        return rep(pe), rep(ne), rep(pp), rep(np_)
 
     def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
         if latents is not None:
@@ -242,7 +259,8 @@ class SD3PredictNextTimeStepModel(nn.Module):
         one trajectory; when omitted the draws are made on the device (the reference calls ``beta_dist.sample()``, :569),
         seeded from ``generator``.  ``return_velocities`` records the per-step CFG velocity (parity tests)."""
         if prompt_embeds is None:
-            self.encode_prompt(prompt=prompt, negative_prompt=negative_prompt)
+            prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = self.encode_prompt(
+                prompt=prompt, negative_prompt=negative_prompt, num_images_per_prompt=num_images_per_prompt)
         if guidance_scale is None:
             raise ValueError("guidance_scale=None is unsupported (as in the reference, whose sigma.repeat(2) is unconditional, :526)")
         if negative_prompt_embeds is None or negative_pooled_prompt_embeds is None or pooled_prompt_embeds is None:

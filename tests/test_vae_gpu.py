@@ -105,3 +105,9 @@ def test_pipeline_returns_images_when_vae_attached():
     ora.load_state_dict({k: v.float() for k, v in model.vae.state_dict().items()})
     ref = ora.decode_latents(out_pt.latents.float())
     assert rel(torch.cat(out_pt.images), ref) < IMG_TOL
+    # :627-643: one image per recorded step and prompt; the last valid step is the image of the default path
+    full = model(**kw, output_type="pt", return_full_process_images=True)
+    T = full.sigmas.shape[1]
+    assert len(full.images) == 2 and full.images[0].shape == (T, 3, 64, 64)
+    lv = int(full.last_valid_indices[0])
+    assert torch.equal(full.images[0][lv], out_pt.images[0][0])

@@ -294,7 +294,13 @@ class SD3PredictNextTimeStepModel(nn.Module):
             finals.append(hist[i, lv])
         finals = torch.stack(finals).to(out_dtype)
         images = []
-        if self.vae is not None and hasattr(self.vae, "decode_latents"):          # :645-655 on the native decoder, one call
+        if return_full_process_images:                                             # :627-643: every step of every prompt
+            if self.vae is None or not hasattr(self.vae, "decode_latents"):
+                raise ValueError("return_full_process_images needs the native VAE decoder (pass vae_config or a checkpoint with vae/)")
+            for i in range(batch_size):
+                steps_i = self.vae.decode_latents(hist[i].to(out_dtype), output_type)   # (T, ...) all recorded steps
+                images.append(list(steps_i) if output_type == "pil" else steps_i)
+        elif self.vae is not None and hasattr(self.vae, "decode_latents"):        # :645-655 on the native decoder, one call
             decoded = self.vae.decode_latents(finals, output_type)
             images = [[im] for im in decoded] if output_type == "pil" else [decoded[i:i + 1] for i in range(batch_size)]
         elif self.vae is not None and hasattr(self.vae, "decode"):                 # a caller-supplied module

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TPDM_ABI_VERSION 1
+#define TPDM_ABI_VERSION 2
 
 typedef enum tpdm_status {
   TPDM_OK = 0,
@@ -53,6 +53,8 @@ typedef struct tpdm_config {
   float min_sigma;
   float epsilon;        /* ratio clamp, 1e-3 (modeling_sd3_pnt.py:197) */
   float tpm_epsilon;    /* exp(x) + 1.0 (modeling_sd3_pnt.py:95,115) */
+  uint64_t dual_attention_mask; /* bit i set = block i is an SD3.5 dual-attention block (attn2 + 9-chunk norm1),
+                                   transformer_sd3.py:104-106,138; 0 for SD3.0 */
 } tpdm_config;
 
 /* Per JointTransformerBlock weights (diffusers state-dict names in comments; D = num_heads*head_dim, dp = head_dim
@@ -78,6 +80,13 @@ typedef struct tpdm_block_weights {
   const float* norm_k;
   const float* norm_added_q;
   const float* norm_added_k;
+  /* dual-attention blocks only (null otherwise): attn2 = self-attention over the image tokens */
+  const void* qkv2_w;   /* bf16 [3*Dp][D]  attn2.to_q | to_k | to_v */
+  const float* qkv2_b;
+  const void* out2_w;   /* bf16 [D][Dp]    attn2.to_out.0 */
+  const float* out2_b;
+  const float* norm_q2; /* [dp] attn2.norm_q.weight, null when qk_norm == 0 */
+  const float* norm_k2;
 } tpdm_block_weights;
 
 typedef struct tpdm_weights {
@@ -94,8 +103,9 @@ typedef struct tpdm_weights {
   const float* p_b2;
   const void* ctx_w;      /* bf16 [D][joint_attention_dim]  context_embedder */
   const float* ctx_b;
-  const void* adaln_w;    /* bf16 [R][D], R = 12*D*L - 2*D: for block i rows [12Di, 12Di+6D) = norm1.linear,
-                             [12Di+6D, ..) = norm1_context.linear (6D rows; last block 2D rows), then norm_out.linear (2D) */
+  const void* adaln_w;    /* bf16 [R][D]: blocks in order, each norm1.linear (6D rows; 9D for a dual-attention block)
+                             followed by norm1_context.linear (6D rows; last block 2D rows), then norm_out.linear (2D).
+                             R = 12*D*L - 2*D + 3*D*popcount(dual_attention_mask) */
   const float* adaln_b;   /* [R] */
   const void* proj_w;     /* bf16 [4*out_channels][D]  proj_out */
   const float* proj_b;

@@ -50,6 +50,7 @@ class SD3Config:
     out_channels: int = 16
     pos_embed_max_size: int = 96
     qk_norm: Optional[str] = None
+    dual_attention_layers: tuple = ()   # () for SD3.0; (0..12) for SD3.5-medium (transformer_sd3.py:104-106)
 
     @property
     def inner_dim(self) -> int:
@@ -213,6 +214,48 @@ class FeedForward(nn.Module):
         return self.net[2](self.net[0](x))
 
 
+class SD35AdaLayerNormZeroX(nn.Module):
+    """diffusers SD35AdaLayerNormZeroX (norm1 of a dual-attention block): 9 chunks
+    shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp, shift_msa2, scale_msa2, gate_msa2; both modulated
+    copies come from the same LayerNorm(x)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.linear = nn.Linear(dim, 9 * dim)
+        self.dim = dim
+
+    def forward(self, x, emb):
+        emb = self.linear(F.silu(emb))
+        shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp, shift_msa2, scale_msa2, gate_msa2 = emb.chunk(9, dim=1)
+        n = F.layer_norm(x, (self.dim,), eps=1e-6)
+        x1 = n * (1 + scale_msa[:, None]) + shift_msa[:, None]
+        x2 = n * (1 + scale_msa2[:, None]) + shift_msa2[:, None]
+        return x1, gate_msa, shift_mlp, scale_mlp, gate_mlp, x2, gate_msa2
+
+
+class SelfAttention(nn.Module):
+    """attn2 of a dual-attention block: diffusers Attention(cross_attention_dim=None, bias=True, qk_norm=...) with
+    JointAttnProcessor2_0 and no encoder states -> plain self-attention over the image tokens."""
+
+    def __init__(self, dim, heads, dim_head, qk_norm):
+        super().__init__()
+        self.heads, self.dim_head = heads, dim_head
+        self.to_q, self.to_k, self.to_v = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Identity()])
+        if qk_norm == "rms_norm":
+            self.norm_q, self.norm_k = RMSNorm(dim_head), RMSNorm(dim_head)
+        self.qk_norm = qk_norm
+
+    def forward(self, x):
+        b, s, _ = x.shape
+        split = lambda t: t.view(b, s, self.heads, self.dim_head).transpose(1, 2)
+        q, k, v = split(self.to_q(x)), split(self.to_k(x)), split(self.to_v(x))
+        if self.qk_norm is not None:
+            q, k = self.norm_q(q), self.norm_k(k)
+        o = F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=False)
+        return self.to_out[0](o.transpose(1, 2).reshape(b, s, self.heads * self.dim_head))
+
+
 class JointAttention(nn.Module):
     """diffusers Attention(added_kv_proj_dim=dim, bias=True) driven by JointAttnProcessor2_0:
     image tokens first, text tokens second; plain softmax(QK^T/sqrt(d))V, no mask."""
@@ -254,25 +297,33 @@ class JointAttention(nn.Module):
 
 
 class JointTransformerBlock(nn.Module):
-    def __init__(self, dim, heads, dim_head, context_pre_only=False, qk_norm=None):
+    def __init__(self, dim, heads, dim_head, context_pre_only=False, qk_norm=None, use_dual_attention=False):
         super().__init__()
         self.context_pre_only = context_pre_only
+        self.use_dual_attention = use_dual_attention
         self.dim = dim
-        self.norm1 = AdaLayerNormZero(dim)
+        self.norm1 = SD35AdaLayerNormZeroX(dim) if use_dual_attention else AdaLayerNormZero(dim)
         self.norm1_context = AdaLayerNormContinuous(dim, dim) if context_pre_only else AdaLayerNormZero(dim)
         self.attn = JointAttention(dim, heads, dim_head, context_pre_only, qk_norm)
+        if use_dual_attention:
+            self.attn2 = SelfAttention(dim, heads, dim_head, qk_norm)
         self.ff = FeedForward(dim)
         if not context_pre_only:
             self.ff_context = FeedForward(dim)
 
     def forward(self, hidden_states, encoder_hidden_states, temb):
-        n, gate_msa, shift_mlp, scale_mlp, gate_mlp = self.norm1(hidden_states, temb)
+        if self.use_dual_attention:
+            n, gate_msa, shift_mlp, scale_mlp, gate_mlp, n2, gate_msa2 = self.norm1(hidden_states, temb)
+        else:
+            n, gate_msa, shift_mlp, scale_mlp, gate_mlp = self.norm1(hidden_states, temb)
         if self.context_pre_only:
             nc = self.norm1_context(encoder_hidden_states, temb)
         else:
             nc, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = self.norm1_context(encoder_hidden_states, temb)
         attn_out, ctx_attn_out = self.attn(n, nc)
         hidden_states = hidden_states + gate_msa.unsqueeze(1) * attn_out
+        if self.use_dual_attention:
+            hidden_states = hidden_states + gate_msa2.unsqueeze(1) * self.attn2(n2)
         m = F.layer_norm(hidden_states, (self.dim,), eps=1e-6) * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
         hidden_states = hidden_states + gate_mlp.unsqueeze(1) * self.ff(m)
         if self.context_pre_only:
@@ -299,7 +350,8 @@ class OracleSD3Transformer(nn.Module):
         self.context_embedder = nn.Linear(cfg.joint_attention_dim, cfg.caption_projection_dim)
         self.transformer_blocks = nn.ModuleList([
             JointTransformerBlock(d, cfg.num_attention_heads, cfg.attention_head_dim,
-                                  context_pre_only=(i == cfg.num_layers - 1), qk_norm=cfg.qk_norm)
+                                  context_pre_only=(i == cfg.num_layers - 1), qk_norm=cfg.qk_norm,
+                                  use_dual_attention=i in tuple(cfg.dual_attention_layers))
             for i in range(cfg.num_layers)])
         self.norm_out = AdaLayerNormContinuous(d, d)
         self.proj_out = nn.Linear(d, cfg.patch_size * cfg.patch_size * cfg.out_channels)

@@ -34,9 +34,9 @@ def test_header_symbols_are_exported(lib):
 def test_abi_version_and_struct_sizes(lib):
     from tpdm_b200 import _lib as L
 
-    assert lib.tpdm_abi_version() == 1
-    assert C.sizeof(L.TpdmConfig) == 13 * 4 + 3 * 4
-    assert C.sizeof(L.TpdmBlockWeights) == 20 * 8
+    assert lib.tpdm_abi_version() == 2
+    assert C.sizeof(L.TpdmConfig) == 13 * 4 + 3 * 4 + 8          # 64 bytes, the uint64 mask is naturally aligned
+    assert C.sizeof(L.TpdmBlockWeights) == 26 * 8
     assert C.sizeof(L.TpdmWeights) == (17 + 1 + 12) * 8
     assert C.sizeof(L.TpdmSampleState) == 11 * 8
 
@@ -101,6 +101,18 @@ def test_state_dict_names_match_reference_layout():
         assert set(a) == set(b), set(a) ^ set(b)
         assert all(a[k].shape == b[k].shape for k in a)
         assert torch.equal(a["pos_embed.pos_embed"], b["pos_embed.pos_embed"])
+    # SD3.5 dual-attention blocks (transformer_sd3.py:104-106,138): attn2.* and a 9-chunk norm1 in the named layers only
+    cfg = O.tiny_config(qk_norm="rms_norm")
+    cfg.dual_attention_layers = (0,)
+    a = O.OracleSD3Transformer(cfg).state_dict()
+    b = CustomSD3Transformer2DModel(sample_size=32, num_layers=2, attention_head_dim=96, num_attention_heads=4, caption_projection_dim=384,
+                                    pos_embed_max_size=96, qk_norm="rms_norm", dual_attention_layers=(0,)).state_dict()
+    assert set(a) == set(b) and all(a[k].shape == b[k].shape for k in a)
+    assert a["transformer_blocks.0.norm1.linear.weight"].shape[0] == 9 * 384 and a["transformer_blocks.1.norm1.linear.weight"].shape[0] == 6 * 384
+    assert "transformer_blocks.0.attn2.norm_q.weight" in b and "transformer_blocks.1.attn2.to_q.weight" not in b
+    with pytest.raises(ValueError):
+        CustomSD3Transformer2DModel(sample_size=32, num_layers=2, attention_head_dim=96, num_attention_heads=4, caption_projection_dim=384,
+                                    dual_attention_layers=(2,))
     tp = TimePredictor(128, 768)
     assert set(tp.state_dict()) == set(O.OracleTimePredictor(128, 768).state_dict())
     assert sorted(tp.state_dict()) == sorted(

@@ -416,3 +416,42 @@ def test_sd3_medium_trajectory_is_deterministic_and_terminates():
     assert torch.isfinite(a.latents).all() and torch.isfinite(a.logprobs).all()
     alpha, beta = a.alphas[0, 0].item(), a.betas[0, 0].item()
     assert abs(float(sig[0]) - (alpha - 1) / (alpha + beta - 2)) < 1e-5     # first step: sigma_1 = 1 * Beta mode
+
+
+@pytest.mark.parametrize("qk_norm,dual", [("rms_norm", (0, 1, 2)), (None, (1,))])
+def test_mmdit_sd35_dual_attention_blocks_vs_oracle(qk_norm, dual):
+    """SURVEY 8(f) rank 4 -- SD3.5 blocks (transformer_sd3.py:104-106,138): 9-chunk norm1, attn2 = image-token self-attention
+    added after the joint attention, optionally QK-RMSNorm; SD3-medium width, 512^2, mixed dual / plain layers incl. the
+    context_pre_only last block."""
+    from oracle import sd3_oracle as O
+    from tpdm_b200.transformer_sd3 import CustomSD3Transformer2DModel
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.sd3_medium_config(sample_size=64, qk_norm=qk_norm)
+    cfg.num_layers = 3
+    cfg.dual_attention_layers = dual
+    torch.manual_seed(99)
+    ora = O.OracleSD3Transformer(cfg).requires_grad_(False).eval().to("cuda")
+    model = CustomSD3Transformer2DModel(sample_size=64, num_layers=3, attention_head_dim=64, num_attention_heads=24, caption_projection_dim=1536,
+                                        pos_embed_max_size=192, qk_norm=qk_norm, dual_attention_layers=dual, device="cuda", dtype=torch.bfloat16)
+    model.load_state_dict(ora.state_dict())
+    ora.load_state_dict(model.state_dict())
+    g = torch.Generator(device="cuda").manual_seed(5)
+    lat = torch.randn(2, 16, 64, 64, device="cuda", generator=g)
+    enc = torch.randn(2, 333, 4096, device="cuda", generator=g)
+    pooled = torch.randn(2, 2048, device="cuda", generator=g)
+    ts = torch.tensor([250.0, 800.0], device="cuda")
+    with torch.no_grad():
+        rv, rt, rh1, rh2 = ora(lat, enc, pooled, ts)
+    v, temb, h1, h2 = model(lat, enc, pooled, ts, return_dict=False)
+    assert rel(temb, rt) < 2e-3 and rel(h2, rh2) < VEL_TOL and rel(v, rv) < VEL_TOL
+    # the attn2 branch really contributes: the same weights with attn2 ignored give a different answer
+    cfg0 = O.sd3_medium_config(sample_size=64, qk_norm=qk_norm)
+    cfg0.num_layers = 3
+    plain = O.OracleSD3Transformer(cfg0).requires_grad_(False).eval().to("cuda")
+    sd = {k: (t[: plain.state_dict()[k].shape[0]] if "norm1.linear" in k else t) for k, t in ora.state_dict().items() if k in plain.state_dict()}
+    plain.load_state_dict(sd)
+    with torch.no_grad():
+        pv = plain(lat, enc, pooled, ts)[0]
+    assert rel(pv, rv) > 5 * rel(v, rv)

@@ -18,11 +18,12 @@ class TpdmConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "num_layers", "num_heads", "head_dim", "joint_attention_dim", "pooled_projection_dim", "in_channels",
         "out_channels", "patch_size", "pos_embed_max_size", "qk_norm", "tpm_channels", "prediction_type", "relative")
-    ] + [("min_sigma", C.c_float), ("epsilon", C.c_float), ("tpm_epsilon", C.c_float)]
+    ] + [("min_sigma", C.c_float), ("epsilon", C.c_float), ("tpm_epsilon", C.c_float), ("dual_attention_mask", C.c_uint64)]
 
 
 BLOCK_FIELDS = ("qkv_w", "qkv_b", "cqkv_w", "cqkv_b", "out_w", "out_b", "cout_w", "cout_b", "ff1_w", "ff1_b", "ff2_w",
-                "ff2_b", "cff1_w", "cff1_b", "cff2_w", "cff2_b", "norm_q", "norm_k", "norm_added_q", "norm_added_k")
+                "ff2_b", "cff1_w", "cff1_b", "cff2_w", "cff2_b", "norm_q", "norm_k", "norm_added_q", "norm_added_k",
+                "qkv2_w", "qkv2_b", "out2_w", "out2_b", "norm_q2", "norm_k2")
 
 
 class TpdmBlockWeights(C.Structure):
@@ -123,7 +124,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.tpdm_abi_version() != 1:
+        if lib.tpdm_abi_version() != 2:
             raise RuntimeError("libtpdm_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -19,6 +19,10 @@ struct tpdm_ctx {
   std::vector<tpdm_block_weights> blocks;
   bool has_weights = false, has_mmdit = false, has_tpm = false;
   int D = 0, dp = 0, Dp = 0, R = 0, device = 0;
+  std::vector<int> mod_off;  // first adaLN row of block i (norm1 rows, then norm1_context rows)
+  bool any_dual = false;
+  bool dual(int i) const { return i < 64 && ((cfg.dual_attention_mask >> i) & 1ull) != 0; }
+  int norm1_rows(int i) const { return (dual(i) ? 9 : 6) * D; }
 };
 
 namespace {
@@ -27,6 +31,9 @@ struct BlockOps {
   GemmOp qkv[2], out[2], ff1[2], ff2[2];
   AttnOp attn;
   int n_streams;  // 2, or 1 for the last (context_pre_only) block
+  bool dual = false;  // SD3.5 dual-attention block: attn2 over the image tokens
+  GemmOp qkv2, out2;
+  AttnOp attn2;
 };
 
 struct Carver {
@@ -50,6 +57,7 @@ struct tpdm_plan {
   // MMDiT activations
   float *x_img, *x_ctx, *ctx0, *mod, *temb, *tproj, *thid, *text_part, *phid, *pout;
   bf16 *xn_img, *xn_ctx, *qkv, *attn_o, *ff_img, *ff_ctx, *enc_bf16;
+  bf16 *xn2_img = nullptr, *qkv2 = nullptr, *attn_o2 = nullptr;  // dual-attention blocks only
   // TimePredictor
   bf16* tpm_x;
   float *y1, *a2, *y2, *tpm_emb, *temb_cfg, *alpha_beta;
@@ -93,6 +101,11 @@ void carve(tpdm_plan* p, Carver& c) {
   p->xn_ctx = c.take<bf16>(Bt * T * D);
   p->qkv = c.take<bf16>(Bt * S * 3 * Dp);
   p->attn_o = c.take<bf16>(Bt * S * Dp);
+  if (ctx->any_dual) {
+    p->xn2_img = c.take<bf16>(Bt * N * D);
+    p->qkv2 = c.take<bf16>(Bt * N * 3 * Dp);
+    p->attn_o2 = c.take<bf16>(Bt * N * Dp);
+  }
   p->ff_img = c.take<bf16>(Bt * N * 4 * D);
   p->ff_ctx = c.take<bf16>(Bt * T * 4 * D);
   p->enc_bf16 = c.take<bf16>(Bt * T * ctx->cfg.joint_attention_dim);
@@ -144,8 +157,9 @@ int build_ops(tpdm_plan* p) {
     BlockOps& o = p->blk[i];
     const bool last = i == L - 1;
     o.n_streams = last ? 1 : 2;
-    float* mod_img = p->mod + static_cast<size_t>(i) * 12 * D;
-    float* mod_ctx = mod_img + 6 * D;
+    float* mod_img = p->mod + ctx->mod_off[i];
+    float* mod_ctx = mod_img + ctx->norm1_rows(i);
+    o.dual = ctx->dual(i);
     // fused QKV: image rows land at tokens [0,N), text rows at [N,S) of the joint qkv buffer
     TPDM_TRY(gemm_op_init(&o.qkv[0], p->xn_img, D, static_cast<long long>(N) * D, N, Bt, D, bw.qkv_w, 3 * Dp, EPI_BIAS_BF16, p->qkv,
                           static_cast<long long>(S) * 3 * Dp, 3 * Dp, bw.qkv_b, nullptr, 0));
@@ -160,6 +174,15 @@ int build_ops(tpdm_plan* p) {
                           p->ff_img, static_cast<long long>(N) * 4 * D, 4 * D, bw.ff1_b, nullptr, 0));
     TPDM_TRY(gemm_op_init(&o.ff2[0], p->ff_img, 4 * D, static_cast<long long>(N) * 4 * D, N, Bt, 4 * D, bw.ff2_w, D, EPI_GATE_RESIDUAL,
                           p->x_img, static_cast<long long>(N) * D, D, bw.ff2_b, mod_img + 5 * D, R));
+    if (o.dual) {
+      // SD3.5 attn2: self-attention over the image tokens from the second modulated copy of LN(x); x += gate_msa2 * (...)
+      TPDM_CHECK(bw.qkv2_w && bw.qkv2_b && bw.out2_w && bw.out2_b, TPDM_ERR_ARG, "block %d: dual-attention block without attn2 weights", i);
+      TPDM_TRY(gemm_op_init(&o.qkv2, p->xn2_img, D, static_cast<long long>(N) * D, N, Bt, D, bw.qkv2_w, 3 * Dp, EPI_BIAS_BF16, p->qkv2,
+                            static_cast<long long>(N) * 3 * Dp, 3 * Dp, bw.qkv2_b, nullptr, 0));
+      TPDM_TRY(attn_op_init(&o.attn2, p->qkv2, Bt, N, ctx->cfg.num_heads, ctx->dp, ctx->cfg.head_dim, p->attn_o2));
+      TPDM_TRY(gemm_op_init(&o.out2, p->attn_o2, Dp, static_cast<long long>(N) * Dp, N, Bt, Dp, bw.out2_w, D, EPI_GATE_RESIDUAL, p->x_img,
+                            static_cast<long long>(N) * D, D, bw.out2_b, mod_img + 8 * D, R));
+    }
     if (!last) {
       TPDM_CHECK(bw.cout_w && bw.cff1_w && bw.cff2_w, TPDM_ERR_ARG, "block %d: missing context-stream weights", i);
       TPDM_TRY(gemm_op_init(&o.out[1], p->attn_o + static_cast<size_t>(N) * Dp, Dp, static_cast<long long>(S) * Dp, T, Bt, Dp, bw.cout_w,
@@ -210,7 +233,7 @@ int run_mmdit(tpdm_plan* p, const float* latents, int Bl, int dup, const float* 
   // kernels leave most of the HBM bandwidth idle: only block 0's rows are computed in line, the rest goes to a side
   // stream that runs underneath block 0 and is joined before block 1 reads its vectors.
   const bf16* aw = reinterpret_cast<const bf16*>(w.adaln_w);
-  const int head_rows = (L > 1 && p->side != nullptr) ? 12 * D : R;
+  const int head_rows = (L > 1 && p->side != nullptr) ? ctx->mod_off[1] : R;
   TPDM_TRY(k_gemv_bf16(aw, w.adaln_b, p->temb, D, nullptr, p->mod, R, Bt, head_rows, D, 1, s));
   if (head_rows < R) {
     TPDM_CUDA_OK(cudaEventRecord(p->ev_fork, s));
@@ -227,13 +250,17 @@ int run_mmdit(tpdm_plan* p, const float* latents, int Bl, int dup, const float* 
     const tpdm_block_weights& bw = ctx->blocks[i];
     const bool last = i == L - 1;
     if (i == 1 && head_rows < R) TPDM_CUDA_OK(cudaStreamWaitEvent(s, p->ev_join, 0));
-    const float* mi = p->mod + static_cast<size_t>(i) * 12 * D;
-    const float* mc = mi + 6 * D;
+    const float* mi = p->mod + ctx->mod_off[i];
+    const float* mc = mi + ctx->norm1_rows(i);
     LnSeg seg[2];
     seg[0] = LnSeg{p->x_img, p->xn_img, mi, mi + D, N, Bt, R};
     // last block: AdaLayerNormContinuous chunk order is (scale, shift)
     seg[1] = last ? LnSeg{p->x_ctx, p->xn_ctx, mc + D, mc, T, Bt, R} : LnSeg{p->x_ctx, p->xn_ctx, mc, mc + D, T, Bt, R};
     TPDM_TRY(k_ln_modulate(seg, 2, D, s));
+    if (o.dual) {  // norm_hidden_states2 = LN(x) * (1 + scale_msa2) + shift_msa2, from x BEFORE the first attention is added
+      LnSeg seg2{p->x_img, p->xn2_img, mi + 6 * D, mi + 7 * D, N, Bt, R};
+      TPDM_TRY(k_ln_modulate(&seg2, 1, D, s));
+    }
     TPDM_TRY(gemm_launch(o.qkv, 2, s));
     if (ctx->cfg.qk_norm) {
       TPDM_TRY(k_qk_rmsnorm(p->qkv, Bt, p->S, 0, N, ctx->cfg.num_heads, ctx->dp, ctx->cfg.head_dim, bw.norm_q, bw.norm_k, s));
@@ -241,13 +268,20 @@ int run_mmdit(tpdm_plan* p, const float* latents, int Bl, int dup, const float* 
     }
     TPDM_TRY(attn_launch(&o.attn, s));
     TPDM_TRY(gemm_launch(o.out, o.n_streams, s));
+    if (o.dual) {
+      TPDM_TRY(gemm_launch(&o.qkv2, 1, s));
+      if (ctx->cfg.qk_norm)
+        TPDM_TRY(k_qk_rmsnorm(p->qkv2, Bt, N, 0, N, ctx->cfg.num_heads, ctx->dp, ctx->cfg.head_dim, bw.norm_q2, bw.norm_k2, s));
+      TPDM_TRY(attn_launch(&o.attn2, s));
+      TPDM_TRY(gemm_launch(&o.out2, 1, s));
+    }
     seg[0] = LnSeg{p->x_img, p->xn_img, mi + 3 * D, mi + 4 * D, N, Bt, R};
     seg[1] = LnSeg{p->x_ctx, p->xn_ctx, mc + 3 * D, mc + 4 * D, T, Bt, R};
     TPDM_TRY(k_ln_modulate(seg, o.n_streams, D, s));
     TPDM_TRY(gemm_launch(o.ff1, o.n_streams, s));
     TPDM_TRY(gemm_launch(o.ff2, o.n_streams, s));
   }
-  const float* mno = p->mod + static_cast<size_t>(L) * 12 * D - 4 * D;  // norm_out rows: (scale, shift)
+  const float* mno = p->mod + (R - 2 * D);  // norm_out rows: (scale, shift)
   const int pairs = tpm_taps ? p->cfg_pairs : 0;
   TPDM_TRY(k_norm_out(p->x_img, p->xn_img, mno + D, mno, R, pairs ? p->B : Bt, pairs, N, D, p->g, p->guidance,
                       tpm_taps ? p->tpm_x : nullptr, h2_out, s));
@@ -301,7 +335,17 @@ int tpdm_create(const tpdm_config* cfg, tpdm_ctx** out) {
   c->D = cfg->num_heads * cfg->head_dim;
   c->dp = cfg->head_dim <= 64 ? 64 : 128;
   c->Dp = cfg->num_heads * c->dp;
-  c->R = 12 * c->D * cfg->num_layers - 2 * c->D;
+  TPDM_CHECK(cfg->num_layers <= 64 || cfg->dual_attention_mask == 0, TPDM_ERR_SHAPE, "dual_attention_mask covers 64 layers at most");
+  TPDM_CHECK(cfg->num_layers >= 64 || (cfg->dual_attention_mask >> cfg->num_layers) == 0, TPDM_ERR_ARG,
+             "dual_attention_mask names a layer >= num_layers");
+  c->mod_off.resize(cfg->num_layers);
+  int rows = 0;
+  for (int i = 0; i < cfg->num_layers; ++i) {
+    c->mod_off[i] = rows;
+    rows += c->norm1_rows(i) + (i == cfg->num_layers - 1 ? 2 : 6) * c->D;
+    c->any_dual = c->any_dual || c->dual(i);
+  }
+  c->R = rows + 2 * c->D;  // + norm_out
   c->device = dev;
   TPDM_CHECK(c->D % 64 == 0 && cfg->joint_attention_dim % 64 == 0, TPDM_ERR_SHAPE, "hidden sizes must be multiples of 64");
   *out = c;
@@ -331,6 +375,9 @@ int tpdm_set_weights(tpdm_ctx* ctx, const tpdm_weights* w) {
                  "tpdm_set_weights: block %d is missing weights", i);
       if (ctx->cfg.qk_norm)
         TPDM_CHECK(b.norm_q && b.norm_k && b.norm_added_q && b.norm_added_k, TPDM_ERR_ARG, "block %d: qk_norm weights missing", i);
+      if (ctx->dual(i))
+        TPDM_CHECK(b.qkv2_w && b.qkv2_b && b.out2_w && b.out2_b && (!ctx->cfg.qk_norm || (b.norm_q2 && b.norm_k2)), TPDM_ERR_ARG,
+                   "block %d: dual-attention block is missing attn2 weights", i);
     }
   }
   if (ctx->has_tpm) {

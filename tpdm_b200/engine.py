@@ -55,6 +55,7 @@ def pack_transformer(pw: PackedWeights, sd: Dict[str, torch.Tensor], cfg, device
     D = H * d
     dp = 64 if d <= 64 else 128
     Lyr = cfg.num_layers
+    dual_layers = set(int(i) for i in (getattr(cfg, "dual_attention_layers", ()) or ()))
     g = lambda k: sd[k].to(device)
     s = pw.struct
     pw._set(s, "patch_w", _f32(g("pos_embed.proj.weight").reshape(D, -1)))
@@ -78,16 +79,16 @@ def pack_transformer(pw: PackedWeights, sd: Dict[str, torch.Tensor], cfg, device
         ada_b += [g(p + "norm1.linear.bias"), g(p + "norm1_context.linear.bias")]
         b = blocks[i]
 
-        def fused(names):
-            w = torch.cat([_pad_heads_rows(g(p + f"attn.{n}.weight"), H, d, dp) for n in names], 0)
-            bias = torch.cat([_pad_heads_rows(g(p + f"attn.{n}.bias"), H, d, dp) for n in names], 0)
+        def fused(names, attn="attn"):
+            w = torch.cat([_pad_heads_rows(g(p + f"{attn}.{n}.weight"), H, d, dp) for n in names], 0)
+            bias = torch.cat([_pad_heads_rows(g(p + f"{attn}.{n}.bias"), H, d, dp) for n in names], 0)
             return _bf16(w), _f32(bias)
 
-        def out_proj(name):
-            w = g(p + f"attn.{name}.weight")  # [D, H*d] -> [D, H*dp]
+        def out_proj(name, attn="attn"):
+            w = g(p + f"{attn}.{name}.weight")  # [D, H*d] -> [D, H*dp]
             if d != dp:
                 w = _pad_heads_rows(w.t().contiguous(), H, d, dp).t().contiguous()
-            return _bf16(w), _f32(g(p + f"attn.{name}.bias"))
+            return _bf16(w), _f32(g(p + f"{attn}.{name}.bias"))
 
         for field, (w, bias) in (("qkv", fused(("to_q", "to_k", "to_v"))), ("cqkv", fused(("add_q_proj", "add_k_proj", "add_v_proj"))),
                                  ("out", out_proj("to_out.0"))):
@@ -105,10 +106,18 @@ def pack_transformer(pw: PackedWeights, sd: Dict[str, torch.Tensor], cfg, device
             pw._set(b, "cff1_b", _f32(g(p + "ff_context.net.0.proj.bias")))
             pw._set(b, "cff2_w", _bf16(g(p + "ff_context.net.2.weight")))
             pw._set(b, "cff2_b", _f32(g(p + "ff_context.net.2.bias")))
+        dual = i in dual_layers
+        if dual:  # SD3.5 attn2 (transformer_sd3.py:138): image-token self-attention with its own projections
+            for field, (w, bias) in (("qkv2", fused(("to_q", "to_k", "to_v"), "attn2")), ("out2", out_proj("to_out.0", "attn2"))):
+                pw._set(b, field + "_w", w)
+                pw._set(b, field + "_b", bias)
         if cfg.qk_norm == "rms_norm":
-            for field, name in (("norm_q", "norm_q"), ("norm_k", "norm_k"), ("norm_added_q", "norm_added_q"),
-                                ("norm_added_k", "norm_added_k")):
-                w = g(p + f"attn.{name}.weight")
+            names = [("norm_q", "attn.norm_q"), ("norm_k", "attn.norm_k"), ("norm_added_q", "attn.norm_added_q"),
+                     ("norm_added_k", "attn.norm_added_k")]
+            if dual:
+                names += [("norm_q2", "attn2.norm_q"), ("norm_k2", "attn2.norm_k")]
+            for field, name in names:
+                w = g(p + f"{name}.weight")
                 wp = w.new_zeros(dp)
                 wp[:d] = w
                 pw._set(b, field, _f32(wp))
@@ -116,7 +125,7 @@ def pack_transformer(pw: PackedWeights, sd: Dict[str, torch.Tensor], cfg, device
     ada_b.append(g("norm_out.linear.bias"))
     pw._set(s, "adaln_w", _bf16(torch.cat(ada_w, 0)))
     pw._set(s, "adaln_b", _f32(torch.cat(ada_b, 0)))
-    assert pw.keep[-1].numel() == 12 * D * Lyr - 2 * D
+    assert pw.keep[-1].numel() == 12 * D * Lyr - 2 * D + 3 * D * len(dual_layers)
     pw.blocks = blocks
     s.blocks = C.cast(blocks, C.POINTER(L.TpdmBlockWeights))
 
@@ -212,7 +221,8 @@ class Engine:
             in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], patch_size=cfg["patch_size"],
             pos_embed_max_size=cfg["pos_embed_max_size"], qk_norm=1 if cfg.get("qk_norm") == "rms_norm" else 0,
             tpm_channels=tpm_channels, prediction_type=0 if prediction_type == "alpha_beta" else 1, relative=1 if relative else 0,
-            min_sigma=min_sigma, epsilon=epsilon, tpm_epsilon=tpm_epsilon)
+            min_sigma=min_sigma, epsilon=epsilon, tpm_epsilon=tpm_epsilon,
+            dual_attention_mask=sum(1 << int(i) for i in set(cfg.get("dual_attention_layers", ()) or ())))
         with torch.cuda.device(device):
             handle = L.vp()
             L.check(lib.tpdm_create(C.byref(c), C.byref(handle)))

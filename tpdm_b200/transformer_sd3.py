@@ -129,13 +129,29 @@ class _FeedForward(nn.Module):
         self.net = nn.ModuleList([_GELUProj(d, **fk), nn.Identity(), nn.Linear(4 * d, d, **fk)])
 
 
+class _SelfAttention(nn.Module):
+    """parameter holder of attn2 in an SD3.5 dual-attention block"""
+
+    def __init__(self, d, dim_head, qk_norm, **fk):
+        super().__init__()
+        for n in ("to_q", "to_k", "to_v"):
+            setattr(self, n, nn.Linear(d, d, **fk))
+        self.to_out = nn.ModuleList([nn.Linear(d, d, **fk), nn.Identity()])
+        if qk_norm == "rms_norm":
+            for n in ("norm_q", "norm_k"):
+                setattr(self, n, _RMSWeight(dim_head, **fk))
+
+
 class _JointBlock(nn.Module):
-    def __init__(self, d, dim_head, context_pre_only, qk_norm, **fk):
+    def __init__(self, d, dim_head, context_pre_only, qk_norm, use_dual_attention=False, **fk):
         super().__init__()
         self.context_pre_only = context_pre_only
-        self.norm1 = _AdaNorm(d, 6, **fk)
+        self.use_dual_attention = use_dual_attention
+        self.norm1 = _AdaNorm(d, 9 if use_dual_attention else 6, **fk)   # SD35AdaLayerNormZeroX : AdaLayerNormZero
         self.norm1_context = _AdaNorm(d, 2 if context_pre_only else 6, **fk)
         self.attn = _Attention(d, dim_head, context_pre_only, qk_norm, **fk)
+        if use_dual_attention:
+            self.attn2 = _SelfAttention(d, dim_head, qk_norm, **fk)
         self.ff = _FeedForward(d, **fk)
         if not context_pre_only:
             self.ff_context = _FeedForward(d, **fk)
@@ -163,8 +179,9 @@ class CustomSD3Transformer2DModel(nn.Module):
         dtype=None,
     ):
         super().__init__()
-        if len(tuple(dual_attention_layers)) != 0:
-            raise ValueError("dual_attention_layers (SD3.5 attn2 blocks) are out of scope for tpdm_b200 (SURVEY.md section 8f)")
+        dual_attention_layers = tuple(int(i) for i in dual_attention_layers)
+        if any(i < 0 or i >= num_layers or i >= 64 for i in dual_attention_layers):
+            raise ValueError(f"dual_attention_layers {dual_attention_layers} must name layers below min(num_layers, 64)")
         if qk_norm not in (None, "rms_norm"):
             raise ValueError(f"unknown qk_norm: {qk_norm}")
         self.config = SimpleNamespace(
@@ -183,7 +200,8 @@ class CustomSD3Transformer2DModel(nn.Module):
         self.time_text_embed = _TimeTextEmbed(d, pooled_projection_dim, **fk)
         self.context_embedder = nn.Linear(joint_attention_dim, caption_projection_dim, **fk)
         self.transformer_blocks = nn.ModuleList(
-            [_JointBlock(d, attention_head_dim, i == num_layers - 1, qk_norm, **fk) for i in range(num_layers)])
+            [_JointBlock(d, attention_head_dim, i == num_layers - 1, qk_norm, use_dual_attention=i in dual_attention_layers, **fk)
+             for i in range(num_layers)])
         self.norm_out = _AdaNorm(d, 2, **fk)
         self.proj_out = nn.Linear(d, patch_size * patch_size * self.out_channels, bias=True, **fk)
         self.gradient_checkpointing = False
@@ -199,7 +217,7 @@ class CustomSD3Transformer2DModel(nn.Module):
         return dict(num_layers=c.num_layers, num_attention_heads=c.num_attention_heads, attention_head_dim=c.attention_head_dim,
                     joint_attention_dim=c.joint_attention_dim, pooled_projection_dim=c.pooled_projection_dim,
                     in_channels=c.in_channels, out_channels=c.out_channels, patch_size=c.patch_size,
-                    pos_embed_max_size=c.pos_embed_max_size, qk_norm=c.qk_norm)
+                    pos_embed_max_size=c.pos_embed_max_size, qk_norm=c.qk_norm, dual_attention_layers=c.dual_attention_layers)
 
     def get_engine(self) -> Engine:
         key = self._weights_key()

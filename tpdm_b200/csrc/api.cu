@@ -70,14 +70,6 @@ struct tpdm_plan {
   unsigned long long seed = 0;
   std::vector<BlockOps> blk;
   GemmOp ctx_embed, proj_out, conv1;
-  // side stream for the HBM-bound adaLN GEMV of blocks 1..L-1, which runs underneath block 0 (see run_mmdit)
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  ~tpdm_plan() {
-    if (ev_fork) cudaEventDestroy(ev_fork);
-    if (ev_join) cudaEventDestroy(ev_join);
-    if (side) cudaStreamDestroy(side);
-  }
 };
 
 namespace {
@@ -229,19 +221,10 @@ int run_mmdit(tpdm_plan* p, const float* latents, int Bl, int dup, const float* 
   TPDM_TRY(k_timestep_embedding(timestep, t_stride, t_scale, p->tproj, Bt, t_rep, s));
   TPDM_TRY(k_gemv_f32(w.t_w1, w.t_b1, p->tproj, 256, nullptr, p->thid, D, Bt, D, 256, 0, s));
   TPDM_TRY(k_gemv_f32(w.t_w2, w.t_b2, p->thid, D, p->text_part, p->temb, D, Bt, D, D, 1, s));
-  // The modulation GEMV streams 1.36 GB of bf16 weights for SD3-medium (0.3 ms at HBM speed) while the tensor-bound block
-  // kernels leave most of the HBM bandwidth idle: only block 0's rows are computed in line, the rest goes to a side
-  // stream that runs underneath block 0 and is joined before block 1 reads its vectors.
-  const bf16* aw = reinterpret_cast<const bf16*>(w.adaln_w);
-  const int head_rows = (L > 1 && p->side != nullptr) ? ctx->mod_off[1] : R;
-  TPDM_TRY(k_gemv_bf16(aw, w.adaln_b, p->temb, D, nullptr, p->mod, R, Bt, head_rows, D, 1, s));
-  if (head_rows < R) {
-    TPDM_CUDA_OK(cudaEventRecord(p->ev_fork, s));
-    TPDM_CUDA_OK(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
-    TPDM_TRY(k_gemv_bf16(aw + static_cast<size_t>(head_rows) * D, w.adaln_b + head_rows, p->temb, D, nullptr, p->mod + head_rows, R, Bt,
-                         R - head_rows, D, 1, p->side));
-    TPDM_CUDA_OK(cudaEventRecord(p->ev_join, p->side));
-  }
+  // (Measured and rejected: running the rows of blocks 1..L-1 on a side stream underneath block 0.  With 8-warp blocks the
+  // GEMV cannot co-reside with a GEMM / attention CTA and nothing overlaps; with 4-warp blocks it does co-reside and the
+  // step got 5-8 % SLOWER -- the resident GEMV blocks delay the CTAs of the tensor-core kernels.)
+  TPDM_TRY(k_gemv_bf16(reinterpret_cast<const bf16*>(w.adaln_w), w.adaln_b, p->temb, D, nullptr, p->mod, R, Bt, R, D, 1, s));
   TPDM_TRY(k_patchify(latents, w.patch_w, w.patch_b, w.pos_table, ctx->cfg.pos_embed_max_size, p->x_img, Bl, dup, ctx->cfg.in_channels,
                       p->Hl, p->Wl, D, h1_out, tpm_taps ? p->tpm_x : nullptr, s));
   TPDM_CUDA_OK(cudaMemcpyAsync(p->x_ctx, p->ctx0, static_cast<size_t>(Bt) * T * D * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -249,7 +232,6 @@ int run_mmdit(tpdm_plan* p, const float* latents, int Bl, int dup, const float* 
     BlockOps& o = p->blk[i];
     const tpdm_block_weights& bw = ctx->blocks[i];
     const bool last = i == L - 1;
-    if (i == 1 && head_rows < R) TPDM_CUDA_OK(cudaStreamWaitEvent(s, p->ev_join, 0));
     const float* mi = p->mod + ctx->mod_off[i];
     const float* mc = mi + ctx->norm1_rows(i);
     LnSeg seg[2];
@@ -431,13 +413,6 @@ int tpdm_plan_create(tpdm_ctx* ctx, int batch, int cfg_pairs, int latent_h, int 
   Carver c(workspace);
   carve(p, c);
   int st = build_ops(p);
-  const char* side_env = std::getenv("TPDM_SIDE_STREAM");
-  if (st == 0 && (side_env == nullptr || side_env[0] != '0')) {
-    if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess)
-      st = fail(TPDM_ERR_CUDA, "tpdm_plan_create: cannot create the side stream: %s", cudaGetErrorString(cudaGetLastError()));
-  }
   if (st != 0) {
     delete p;
     return st;

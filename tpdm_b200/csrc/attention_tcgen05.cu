@@ -278,29 +278,28 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       alpha_pending = 1.f;
       bool fast_ok = false;
       if (i > 0 && valid >= kHT) {
-        // ---- fast path: one pass with the (possibly stale) running max; the half-tile's own max is tracked on the side
+        // ---- fast path: one pass against the reference max m_used, which is NOT updated here.  fp32 sums and bf16 P carry an
+        // 8-bit exponent, so p = 2^(s - m_used) stays exact in relative terms however far the true row max has moved past
+        // m_used -- until 2^128.  Overflow is detected after the fact (an infinite row sum) BEFORE P is published; S[bb] is
+        // released only after that check, so the exact route below can redo the half-tile and move m_used.  This drops the
+        // 32 FMNMX3 and their dependent chain per half-tile that tracking the tile's own max cost.
         const uint64_t l_save = l2;
         const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
         uint32_t va[32], vb[32];
         tmem_ld_32x32(s_tmem, va);
         tmem_wait_ld();
         tmem_ld_32x32(s_tmem + 32, vb);
-        float tmax = chunk_max(va, -INFINITY);
         exp_chunk(va, p_tmem, negm2, true);
         tmem_wait_ld();
-        tmax = chunk_max(vb, tmax);
-        const float grow = tmax * scale - m_used;
-        if (!__any_sync(0xffffffffu, grow > 100.f)) {  // exp2 cannot overflow: accept
+        exp_chunk(vb, p_tmem + 16, negm2, true);
+        float l_lo, l_hi;
+        unpack_f32x2(l2, l_lo, l_hi);
+        const bool overflow = !(l_lo + l_hi < 1e37f);  // inf, NaN, or close enough to the bf16 / fp32 limit to round to inf
+        if (!__any_sync(0xffffffffu, overflow)) {
           fast_ok = true;
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_free[bb]);
-          exp_chunk(vb, p_tmem + 16, negm2, true);
-          if (grow > kRescaleThreshold) {
-            need_pending = true;
-            alpha_pending = exp2_approx(-grow);
-            m_used = tmax * scale;
-          }
         } else {
           l2 = l_save;  // S[bb] is still intact (s_free not signalled): redo on the exact route
         }

@@ -19,6 +19,13 @@
 // running max (exact: the final 1/l normalisation cancels it); when a half-tile raises the max by more than 2^8 the
 // accumulator O and the row sum are rescaled once the outstanding P V has drained; the first half-tile, the masked tail
 // and (never observed) jumps above 2^100 take an exact two-pass route.
+//
+// Where the time goes (ncu source-level samples, profiles/r01_attention_ncu.txt): per 64-key half-tile and CTA the kernel
+// needs 512 cycles of the MUFU pipe (ex2, 16 / clk / SM) AND 512 cycles of the TMEM read port (S in fp32, 64 B / clk / SM)
+// -- both floors are 214 us for S = 4429, H = 24, Bt = 2 -- against 256 cycles of tensor pipe; it runs at 61 % of either.
+// Measured and rejected: tracking the half-tile's own max (32 FMNMX3 per row and half-tile; removing it changed nothing,
+// so it was dropped), 8 softmax warps with the columns of a half-tile split between two warps per lane quarter (360 us
+// stand-alone, 3 % slower in the trajectory), a second MMA-issuing warp for P V (kept, +2 %).
 #include <cuda_bf16.h>
 
 #include "common.cuh"

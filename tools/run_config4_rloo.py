@@ -37,6 +37,7 @@ def main():
     data = w.rloo_repeat(data, k)
     trainer = TimePredictorTrainer(w.agent_model.time_predictor, grid=32, max_samples=8 * 28, lr=1e-6)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    w.sample({**data, "predict": False, "generator": torch.Generator().manual_seed(1)})   # warm-up: weight packing, plan, first launches
     torch.cuda.synchronize()
     ev[0].record()
     out = w.sample({**data, "predict": False, "generator": torch.Generator().manual_seed(7 + rank * 100003)})
@@ -82,6 +83,8 @@ def main():
         print(json.dumps({"config": "SD3-medium 512^2 RLOO rollout, 4 prompts x rloo_k 4 per GPU, micro-batch 8" + (" [2 blocks]" if small else ""),
                           "n_gpus": world, "rollout_ms": ev[0].elapsed_time(ev[1]), "rollout_steps": T,
                           "rollouts_per_s_all_gpus": world * 16 / (ev[0].elapsed_time(ev[1]) / 1e3),
+                          "ms_per_denoise_step": ev[0].elapsed_time(ev[1]) / T,
+                          "mmdit_tflops": 67.44 * T / ev[0].elapsed_time(ev[1]) * 1e3 if not small else None,
                           "adamw_ms": ev[2].elapsed_time(ev[3]), "grad_norm": float(gn), "loss": float(st["loss"]),
                           "allreduce_bytes": trainer.grads.numel() * 4, "checks": "allreduce == sum of rank grads; params identical across ranks"}))
     if world > 1:

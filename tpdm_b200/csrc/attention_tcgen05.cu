@@ -25,7 +25,9 @@
 // -- both floors are 214 us for S = 4429, H = 24, Bt = 2 -- against 256 cycles of tensor pipe; it runs at 61 % of either.
 // Measured and rejected: tracking the half-tile's own max (32 FMNMX3 per row and half-tile; removing it changed nothing,
 // so it was dropped), 8 softmax warps with the columns of a half-tile split between two warps per lane quarter (360 us
-// stand-alone, 3 % slower in the trajectory), a second MMA-issuing warp for P V (kept, +2 %).
+// stand-alone, 3 % slower in the trajectory), prefetching the next half-tile's first 32 S columns during the second
+// exponential block (398 us: 128 registers and spills), a second MMA-issuing warp for P V (kept, +2 %).  With the
+// exponentials compiled out the kernel still takes 260 us, so MUFU and the TMEM-read side are about equally loaded.
 #include <cuda_bf16.h>
 
 #include "common.cuh"

@@ -233,6 +233,28 @@ int tpdm_adamw_step(float* params, const float* grads, float* m, float* v, long 
 
 /* ---- measurement hooks used by bench.py -------------------------------------------------------------------------- */
 /* ----------------------------------------------------------------------------------------------------------------
+ * Device-side prompt queue (BASELINE config 3: prompts with different trajectory lengths).  The plan's `batch` entries are
+ * in-flight SLOTS.  Every prompt runs the same per-prompt trajectory as tpdm_sample_* with batch 1 and predict = 1
+ * (modeling_sd3_pnt.py:522-612: the prompt stops at the first sigma_next < min_sigma or at max_steps); a slot whose prompt
+ * ended writes its final latent to out_latents[prompt], takes the next ticket (atomicAdd, system scope) and starts on that
+ * prompt in the next step -- no host round trip, no collective.  `ticket` is a device-visible int the owner zeroes
+ * beforehand; several GPUs of one box share the prompt list by sharing that counter (CUDA IPC / peer memory).
+ *   latents_all [P][C][h][w], *_embeds_all [P][T][joint_attention_dim], *_pooled_all [P][pooled_projection_dim]: all P
+ *   prompts resident on the device (borrowed until the queue has drained).  Outputs: out_latents [P][C][h][w] (rows of
+ *   prompts this plan did not process are left untouched), out_steps [P], out_sigmas [P][max_steps + 1] or NULL.
+ * ---------------------------------------------------------------------------------------------------------------- */
+size_t tpdm_queue_workspace_bytes(const tpdm_plan* plan, int n_prompts);
+int tpdm_queue_begin(tpdm_plan* plan, int n_prompts, const float* latents_all, const float* neg_embeds_all,
+                     const float* pos_embeds_all, const float* neg_pooled_all, const float* pos_pooled_all,
+                     float guidance_scale, void* queue_workspace, size_t queue_workspace_bytes, int* ticket,
+                     float* out_latents, int* out_steps, float* out_sigmas, void* stream);
+/* one denoising step of every occupied slot, then retire / refill.  No host synchronisation. */
+int tpdm_queue_step(tpdm_plan* plan, void* stream);
+/* device pointers: *active_slots -> int, slots holding a prompt after the last enqueued step (0 = drained);
+ * *slot_prompts -> int[batch] */
+int tpdm_queue_status(tpdm_plan* plan, const int** active_slots, const int** slot_prompts);
+
+/* ----------------------------------------------------------------------------------------------------------------
  * VAE decode of the final latent.  Replaces, for the decode step only,
  *   latents = latents / vae.config.scaling_factor + vae.config.shift_factor
  *   image   = vae.decode(latents, return_dict=False)[0];  image_processor.postprocess(image, "pil")

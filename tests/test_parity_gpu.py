@@ -455,3 +455,53 @@ def test_mmdit_sd35_dual_attention_blocks_vs_oracle(qk_norm, dual):
     with torch.no_grad():
         pv = plain(lat, enc, pooled, ts)[0]
     assert rel(pv, rv) > 5 * rel(v, rv)
+
+
+def test_device_prompt_queue_matches_per_prompt_sampling():
+    """BASELINE config 3 mechanism: 7 prompts with different trajectory lengths through 3 in-flight slots refilled on the
+    device == each prompt sampled alone (batch 1, predict=True): same step counts, same sigma sequences, same final latents.
+    Two 'GPUs' sharing one ticket counter split the list without overlap."""
+    from oracle import sd3_oracle as O
+    from tpdm_b200.modeling_sd3_pnt import SD3PredictNextTimeStepModel
+
+    tiny = dict(sample_size=32, patch_size=2, in_channels=16, num_layers=2, attention_head_dim=96, num_attention_heads=4,
+                joint_attention_dim=4096, caption_projection_dim=384, pooled_projection_dim=2048, out_channels=16, pos_embed_max_size=96)
+    torch.manual_seed(21)
+    model = SD3PredictNextTimeStepModel(transformer_config=tiny, torch_dtype=torch.float32, device="cuda", min_sigma=0.05)
+    with torch.no_grad():      # make the TimePredictor depend on its input so that trajectory lengths differ between prompts
+        tp = model.time_predictor
+        tp.fc2.weight.mul_(40)
+        tp.fc1.weight.mul_(8)
+        tp.conv2.weight.mul_(6)
+        tp.norm1.linear.weight.mul_(4)
+    P, T = 7, 12
+    g = torch.Generator().manual_seed(3)
+    mk = lambda *s: torch.randn(*s, generator=g).cuda()
+    pe, ne, pp, npp, lat = mk(P, 333, 4096), mk(P, 333, 4096), mk(P, 2048), mk(P, 2048), mk(P, 16, 32, 32)
+    lat = lat * torch.linspace(0.5, 2.0, P, device="cuda").view(P, 1, 1, 1)     # different inputs -> different alpha/beta
+    ref_steps, ref_lat, ref_sig = [], [], []
+    for i in range(P):
+        o = model(prompt_embeds=pe[i:i + 1], negative_prompt_embeds=ne[i:i + 1], pooled_prompt_embeds=pp[i:i + 1],
+                  negative_pooled_prompt_embeds=npp[i:i + 1], latents=lat[i:i + 1], max_inference_steps=T, predict=True)
+        ref_steps.append(o.sigmas.shape[1])
+        ref_lat.append(o.latents[0])
+        ref_sig.append(o.sigmas[0])
+    assert len(set(ref_steps)) > 1, ref_steps          # the stress is real: lengths differ
+    q = model.sample_queue(pe, ne, pp, npp, latents=lat, slots=3, max_inference_steps=T)
+    assert q.steps.tolist() == ref_steps
+    for i in range(P):
+        n = ref_steps[i]
+        assert torch.allclose(q.sigmas[i, 1:n + 1], ref_sig[i], atol=1e-5)
+        assert rel(q.latents[i], ref_lat[i]) < 1e-4
+    # fewer device steps than running the prompts one after the other, and no more than slots allow
+    assert q.device_steps < sum(ref_steps) and q.device_steps >= -(-sum(ref_steps) // 3)
+    # two workers sharing one ticket counter: every prompt is processed exactly once
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    a = model.sample_queue(pe, ne, pp, npp, latents=lat, slots=2, max_inference_steps=T, ticket=ticket)
+    assert int(ticket) >= P and a.steps.tolist() == ref_steps     # a single worker drains the shared counter completely
+    ticket.zero_()
+    ticket += 4                                                   # another worker already took prompts 0..3
+    b = model.sample_queue(pe, ne, pp, npp, latents=lat, slots=2, max_inference_steps=T, ticket=ticket)
+    assert b.steps.tolist() == [0, 0, 0, 0] + ref_steps[4:]
+    with pytest.raises(ValueError):
+        model.sample_queue(pe, ne, pp, npp, latents=lat, slots=P + 1, max_inference_steps=T)

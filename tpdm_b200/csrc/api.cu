@@ -70,6 +70,14 @@ struct tpdm_plan {
   unsigned long long seed = 0;
   std::vector<BlockOps> blk;
   GemmOp ctx_embed, proj_out, conv1;
+  // device-side prompt queue (tpdm_queue_*): the plan's batch entries are in-flight slots
+  struct Queue {
+    int n_prompts = 0, begun = 0;
+    const float* noise_all = nullptr;
+    float *ctx0_all = nullptr, *text_all = nullptr, *sigma_cur = nullptr, *sigma_next = nullptr, *out_latents = nullptr, *out_sigmas = nullptr;
+    int *slot_prompt = nullptr, *slot_step = nullptr, *slot_flush = nullptr, *slot_load = nullptr, *ticket = nullptr, *out_steps = nullptr,
+        *active = nullptr, *idle_flag = nullptr;
+  } q;
 };
 
 namespace {
@@ -537,6 +545,140 @@ int tpdm_sample_state_get(tpdm_plan* p, tpdm_sample_state* out) {
   out->tembs = p->tembs;
   out->tpm_input = p->tpm_x;
   out->history_latents = p->history;
+  return 0;
+}
+
+// ---- device-side prompt queue ------------------------------------------------------------------------------------
+namespace {
+size_t queue_bytes(const tpdm_plan* p, int n_prompts) {
+  const size_t ctx = static_cast<size_t>(p->T) * p->ctx->D, D = p->ctx->D, B = p->B;
+  Carver c(nullptr);
+  c.take<float>(static_cast<size_t>(n_prompts) * 2 * ctx);
+  c.take<float>(static_cast<size_t>(n_prompts) * 2 * D);
+  c.take<float>(2 * B);
+  c.take<int>(4 * B + 8);
+  return c.off + 1024;
+}
+QueueArgs queue_args(const tpdm_plan* p, int init) {
+  const tpdm_plan::Queue& q = p->q;
+  QueueArgs a{};
+  a.alpha_beta = p->alpha_beta;
+  a.sigma_cur = q.sigma_cur;
+  a.sigma_next = q.sigma_next;
+  a.slot_prompt = q.slot_prompt;
+  a.slot_step = q.slot_step;
+  a.slot_flush = q.slot_flush;
+  a.slot_load = q.slot_load;
+  a.ticket = q.ticket;
+  a.out_steps = q.out_steps;
+  a.out_sigmas = q.out_sigmas;
+  a.active = q.active;
+  a.idle_flag = q.idle_flag;
+  a.B = p->B;
+  a.n_prompts = q.n_prompts;
+  a.max_steps = p->max_steps;
+  a.relative = p->ctx->cfg.relative;
+  a.prediction_type = p->ctx->cfg.prediction_type;
+  a.init = init;
+  a.min_sigma = p->ctx->cfg.min_sigma;
+  a.epsilon = p->ctx->cfg.epsilon;
+  return a;
+}
+int queue_move(tpdm_plan* p, cudaStream_t s) {
+  const tpdm_plan::Queue& q = p->q;
+  const long long lat = static_cast<long long>(p->ctx->cfg.in_channels) * p->Hl * p->Wl, ctx = static_cast<long long>(p->T) * p->ctx->D;
+  return k_queue_move(q.slot_prompt, q.slot_flush, q.slot_load, p->B, lat, ctx, p->ctx->D, p->latents, q.noise_all, q.out_latents, p->ctx0,
+                      q.ctx0_all, p->text_part, q.text_all, s);
+}
+}  // namespace
+
+size_t tpdm_queue_workspace_bytes(const tpdm_plan* p, int n_prompts) {
+  if (!p || n_prompts <= 0) return 0;
+  return queue_bytes(p, n_prompts);
+}
+
+int tpdm_queue_begin(tpdm_plan* p, int n_prompts, const float* latents_all, const float* neg_embeds_all, const float* pos_embeds_all,
+                     const float* neg_pooled_all, const float* pos_pooled_all, float guidance_scale, void* queue_workspace,
+                     size_t queue_workspace_bytes, int* ticket, float* out_latents, int* out_steps, float* out_sigmas, void* stream) {
+  TPDM_CHECK(p && latents_all && neg_embeds_all && pos_embeds_all && neg_pooled_all && pos_pooled_all && queue_workspace && ticket &&
+                 out_latents && out_steps,
+             TPDM_ERR_ARG, "tpdm_queue_begin: null argument");
+  TPDM_CHECK(p->cfg_pairs, TPDM_ERR_STATE, "tpdm_queue_begin: the plan was created without cfg_pairs");
+  TPDM_CHECK(p->ctx->has_mmdit && p->ctx->has_tpm, TPDM_ERR_STATE, "tpdm_queue_begin: needs both MMDiT and TimePredictor weights");
+  TPDM_CHECK(n_prompts >= p->B, TPDM_ERR_ARG, "tpdm_queue_begin: %d prompts for %d slots (use a plan with fewer slots)", n_prompts, p->B);
+  TPDM_CHECK((reinterpret_cast<uintptr_t>(queue_workspace) & 1023) == 0 && queue_workspace_bytes >= queue_bytes(p, n_prompts), TPDM_ERR_ARG,
+             "tpdm_queue_begin: queue workspace must be 1 KiB aligned and >= %zu bytes", queue_bytes(p, n_prompts));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const tpdm_ctx* ctx = p->ctx;
+  const int B = p->B, D = ctx->D, T = p->T, J = ctx->cfg.joint_attention_dim, PD = ctx->cfg.pooled_projection_dim;
+  const size_t nctx = static_cast<size_t>(T) * D;
+  tpdm_plan::Queue& q = p->q;
+  Carver c(queue_workspace);
+  q.ctx0_all = c.take<float>(static_cast<size_t>(n_prompts) * 2 * nctx);
+  q.text_all = c.take<float>(static_cast<size_t>(n_prompts) * 2 * D);
+  q.sigma_cur = c.take<float>(2 * B);
+  q.sigma_next = q.sigma_cur + B;
+  q.slot_prompt = c.take<int>(4 * B + 8);
+  q.slot_step = q.slot_prompt + B;
+  q.slot_flush = q.slot_step + B;
+  q.slot_load = q.slot_flush + B;
+  q.active = q.slot_load + B;
+  q.idle_flag = q.active + 1;
+  q.n_prompts = n_prompts;
+  q.noise_all = latents_all;
+  q.ticket = ticket;
+  q.out_latents = out_latents;
+  q.out_steps = out_steps;
+  q.out_sigmas = out_sigmas;
+  p->guidance = guidance_scale;
+  p->predict = 1;
+  // sigma-independent text branch of every prompt, B prompts at a time through the plan's own buffers
+  // (context_embedder + pooled-text MLP: transformer_sd3.py:337 and half of :336), parked per prompt as (uncond, cond)
+  for (int c0 = 0; c0 < n_prompts; c0 += B) {
+    const int start = c0 + B <= n_prompts ? c0 : n_prompts - B;  // the last chunk overlaps the previous one
+    TPDM_TRY(set_prompts(p, neg_embeds_all + static_cast<size_t>(start) * T * J, pos_embeds_all + static_cast<size_t>(start) * T * J,
+                         neg_pooled_all + static_cast<size_t>(start) * PD, pos_pooled_all + static_cast<size_t>(start) * PD, s));
+    for (int b = 0; b < B; ++b)
+      for (int half = 0; half < 2; ++half) {
+        const size_t src = static_cast<size_t>(half) * B + b, dst = static_cast<size_t>(start + b) * 2 + half;
+        TPDM_CUDA_OK(cudaMemcpyAsync(q.ctx0_all + dst * nctx, p->ctx0 + src * nctx, nctx * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        TPDM_CUDA_OK(cudaMemcpyAsync(q.text_all + dst * D, p->text_part + src * D, D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      }
+  }
+  TPDM_CUDA_OK(cudaMemsetAsync(q.slot_prompt, 0xff, sizeof(int) * B, s));  // -1: every slot is idle and asks for a ticket
+  TPDM_CUDA_OK(cudaMemsetAsync(q.slot_step, 0, sizeof(int) * (3 * B + 8), s));
+  TPDM_TRY(k_queue_advance(queue_args(p, 1), s));
+  TPDM_TRY(queue_move(p, s));
+  q.begun = 1;
+  p->begun = 0;  // the per-batch sampler state is not valid while the queue owns the plan
+  return 0;
+}
+
+int tpdm_queue_step(tpdm_plan* p, void* stream) {
+  TPDM_CHECK(p, TPDM_ERR_ARG, "tpdm_queue_step: null plan");
+  TPDM_CHECK(p->q.begun, TPDM_ERR_STATE, "tpdm_queue_step: call tpdm_queue_begin first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const tpdm_ctx* ctx = p->ctx;
+  const int B = p->B;
+  // a step enqueued after the queue drained (idle_flag set) turns into empty launches
+  set_skip_flag(p->q.idle_flag);
+  int st_mm = run_mmdit(p, p->latents, B, 2, p->q.sigma_cur, 1, 1000.0f, 2, nullptr, nullptr, true, s);
+  set_skip_flag(nullptr);
+  TPDM_TRY(st_mm);
+  TPDM_TRY(k_cfg_combine(p->temb, p->temb_cfg, nullptr, B, ctx->D, p->guidance, s));
+  TPDM_TRY(run_tpm(p, B, p->temb_cfg, p->alpha_beta, s));
+  TPDM_TRY(k_queue_schedule(queue_args(p, 0), s));
+  TPDM_TRY(k_unpatchify(p->pout, B, 1, p->guidance, ctx->cfg.out_channels, p->Hl, p->Wl, nullptr, p->latents, p->q.sigma_cur,
+                        p->q.sigma_next, 1, nullptr, s));
+  TPDM_TRY(k_queue_advance(queue_args(p, 0), s));
+  TPDM_TRY(queue_move(p, s));
+  return 0;
+}
+
+int tpdm_queue_status(tpdm_plan* p, const int** active_slots, const int** slot_prompts) {
+  TPDM_CHECK(p && p->q.begun, TPDM_ERR_STATE, "tpdm_queue_status: call tpdm_queue_begin first");
+  if (active_slots) *active_slots = p->q.active;
+  if (slot_prompts) *slot_prompts = p->q.slot_prompt;
   return 0;
 }
 

@@ -718,6 +718,100 @@ __global__ void schedule_kernel(const ScheduleArgs a) {
   if (i == 0) a.all_done[a.step] = all;
 }
 
+// ---- device-side prompt queue ---------------------------------------------------------------------------------
+// predict-mode schedule update per slot (modeling_sd3_pnt.py:557-590 with ratio = Beta mode), sigma kept per slot
+__global__ void queue_schedule_kernel(const QueueArgs a) {
+  const int i = threadIdx.x;
+  if (i >= a.B) return;
+  const float p1 = a.alpha_beta[2 * i], p2 = a.alpha_beta[2 * i + 1];
+  float alpha = p1, beta = p2;
+  if (a.prediction_type != 0) {
+    alpha = p1 * (p2 - 2.f) + 1.f;
+    beta = (1.f - p1) * (p2 - 2.f) + 1.f;
+  }
+  const float sigma = a.sigma_cur[i];
+  float ratio = (alpha - 1.f) / (alpha + beta - 2.f);
+  float sigma_next;
+  if (a.relative) {
+    ratio = fminf(fmaxf(ratio, a.epsilon), 1.f - a.epsilon);
+    sigma_next = sigma * ratio;
+  } else {
+    ratio = fminf(fmaxf(ratio, a.epsilon), sigma);
+    ratio = fminf(fmaxf(ratio, 0.f), 1.f - a.epsilon);
+    sigma_next = sigma - ratio;
+  }
+  if (sigma < a.min_sigma) sigma_next = 0.f;
+  if (a.slot_prompt[i] < 0) sigma_next = sigma;  // idle slot: the Euler step is a no-op
+  a.sigma_next[i] = sigma_next;
+}
+
+// after the Euler step: count the step, retire finished trajectories, hand the freed slots their next ticket
+__global__ void queue_advance_kernel(const QueueArgs a) {
+  const int i = threadIdx.x;
+  int holds = 0;
+  if (i < a.B) {
+    int prompt = a.slot_prompt[i], flush = -1, load = 0;
+    bool need = a.init != 0;
+    if (!a.init && prompt >= 0) {
+      const int step = a.slot_step[i] + 1;
+      const float sn = a.sigma_next[i];
+      if (a.out_sigmas) a.out_sigmas[static_cast<long long>(prompt) * (a.max_steps + 1) + step] = sn;
+      if (sn < a.min_sigma || step >= a.max_steps) {   // the prompt-level form of the batch-wide exit test (:608)
+        flush = prompt;
+        a.out_steps[prompt] = step;
+        need = true;
+      } else {
+        a.slot_step[i] = step;
+        a.sigma_cur[i] = sn;
+      }
+    }
+    if (need) {
+      const int t = atomicAdd_system(a.ticket, 1);
+      prompt = t < a.n_prompts ? t : -1;
+      a.slot_prompt[i] = prompt;
+      a.slot_step[i] = 0;
+      a.sigma_cur[i] = 1.0f;                            // sigma = ones (:508)
+      load = prompt >= 0 ? 1 : 0;
+      if (prompt >= 0 && a.out_sigmas) a.out_sigmas[static_cast<long long>(prompt) * (a.max_steps + 1)] = 1.0f;
+    }
+    a.slot_flush[i] = flush;
+    a.slot_load[i] = load;
+    holds = prompt >= 0 ? 1 : 0;
+  }
+  const int n = __syncthreads_count(holds);
+  if (i == 0) {
+    *a.active = n;
+    *a.idle_flag = n == 0 ? 1 : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) queue_move_kernel(const int* __restrict__ slot_prompt, const int* __restrict__ slot_flush,
+                                                         const int* __restrict__ slot_load, int B, long long lat, long long ctx, int D,
+                                                         float* __restrict__ latents, const float* __restrict__ noise_all,
+                                                         float* __restrict__ out_latents, float* __restrict__ ctx0,
+                                                         const float* __restrict__ ctx0_all, float* __restrict__ text_part,
+                                                         const float* __restrict__ text_all) {
+  const int b = blockIdx.y;
+  const int flush = slot_flush[b], load = slot_load[b], prompt = slot_prompt[b];
+  if (flush < 0 && !load) return;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x * 4;
+  const long long t0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (flush >= 0)
+    for (long long k = t0; k < lat; k += stride)
+      *reinterpret_cast<float4*>(out_latents + flush * lat + k) = ld4(latents + b * lat + k);
+  if (load) {
+    for (long long k = t0; k < lat; k += stride) *reinterpret_cast<float4*>(latents + b * lat + k) = ld4(noise_all + prompt * lat + k);
+    for (int half = 0; half < 2; ++half) {
+      float* dst = ctx0 + (static_cast<long long>(half) * B + b) * ctx;
+      const float* src = ctx0_all + (static_cast<long long>(prompt) * 2 + half) * ctx;
+      for (long long k = t0; k < ctx; k += stride) *reinterpret_cast<float4*>(dst + k) = ld4(src + k);
+      float* tdst = text_part + (static_cast<long long>(half) * B + b) * D;
+      const float* tsrc = text_all + (static_cast<long long>(prompt) * 2 + half) * D;
+      for (long long k = t0; k < D; k += stride) *reinterpret_cast<float4*>(tdst + k) = ld4(tsrc + k);
+    }
+  }
+}
+
 inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
 
 }  // namespace
@@ -874,6 +968,33 @@ int k_tpm_tail(const float* y2, int B, int go, int C, const float* fc1_w, const 
                float eps, float* alpha_beta, cudaStream_t s) {
   TPDM_CHECK(C <= 128 && C % 32 == 0, TPDM_ERR_SHAPE, "tpm_tail: conv_out_channels %d must be a multiple of 32, <= 128", C);
   tpm_tail_kernel<<<B, 1024, 0, s>>>(y2, go, C, fc1_w, fc1_b, fc2_w, fc2_b, eps, alpha_beta);
+  count_launch();
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_queue_schedule(const QueueArgs& a, cudaStream_t s) {
+  TPDM_CHECK(a.B <= 1024, TPDM_ERR_SHAPE, "queue: %d slots > 1024", a.B);
+  queue_schedule_kernel<<<1, ((a.B + 31) / 32) * 32, 0, s>>>(a);
+  count_launch();
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_queue_advance(const QueueArgs& a, cudaStream_t s) {
+  TPDM_CHECK(a.B <= 1024, TPDM_ERR_SHAPE, "queue: %d slots > 1024", a.B);
+  queue_advance_kernel<<<1, ((a.B + 31) / 32) * 32, 0, s>>>(a);
+  count_launch();
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_queue_move(const int* slot_prompt, const int* slot_flush, const int* slot_load, int B, long long lat, long long ctx, int D,
+                 float* latents, const float* noise_all, float* out_latents, float* ctx0, const float* ctx0_all, float* text_part,
+                 const float* text_all, cudaStream_t s) {
+  TPDM_CHECK(lat % 4 == 0 && ctx % 4 == 0 && D % 4 == 0, TPDM_ERR_SHAPE, "queue: sizes must be multiples of 4 floats");
+  queue_move_kernel<<<dim3(64, B), 256, 0, s>>>(slot_prompt, slot_flush, slot_load, B, lat, ctx, D, latents, noise_all, out_latents, ctx0, ctx0_all,
+                                               text_part, text_all);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

@@ -77,4 +77,29 @@ struct ScheduleArgs {
 };
 int k_schedule(const ScheduleArgs& a, cudaStream_t s);
 
+// ---- device-side prompt queue (continuous batching over a fixed number of in-flight slots) ---------------------------
+struct QueueArgs {
+  const float* alpha_beta;   // [B][2] TimePredictor outputs of this step
+  float* sigma_cur;          // [B] sigma the step was run at; advanced / reset in queue_advance
+  float* sigma_next;         // [B] written by queue_schedule, consumed by the Euler step
+  int* slot_prompt;          // [B] prompt id in flight, -1 = idle
+  int* slot_step;            // [B] steps done on that prompt
+  int* slot_flush;           // [B] out: prompt id whose final latent must be written out (-1: none)
+  int* slot_load;            // [B] out: 1 = a new prompt was assigned to the slot (its inputs must be loaded)
+  int* ticket;               // next prompt id; may live in peer / pinned memory shared by several GPUs
+  int* out_steps;            // [P]
+  float* out_sigmas;         // [P][max_steps + 1] or null
+  int* active;               // [1] slots that hold a prompt after this step
+  int* idle_flag;            // [1] 1 when active == 0 (skip flag of the next, speculatively enqueued step)
+  int B, n_prompts, max_steps, relative, prediction_type, init;
+  float min_sigma, epsilon;
+};
+int k_queue_schedule(const QueueArgs& a, cudaStream_t s);
+int k_queue_advance(const QueueArgs& a, cudaStream_t s);
+// per slot b: flush -> out_latents[flush] = latents[b]; load -> latents[b] = noise_all[prompt], ctx0 / text_part rows b and B + b
+// = ctx0_all / text_all [prompt][0 | 1]
+int k_queue_move(const int* slot_prompt, const int* slot_flush, const int* slot_load, int B, long long lat, long long ctx, int D,
+                 float* latents, const float* noise_all, float* out_latents, float* ctx0, const float* ctx0_all, float* text_part,
+                 const float* text_all, cudaStream_t s);
+
 }  // namespace tpdm

@@ -367,3 +367,53 @@ class Engine:
         if vel is not None:
             out["velocities"] = vel[:, :T]
         return out
+
+    def sample_queue(self, latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
+                     slots: int, max_inference_steps: int, guidance_scale: float, ticket: Optional[torch.Tensor] = None,
+                     out_latents: Optional[torch.Tensor] = None):
+        """Device-side prompt queue (``tpdm_queue_*``): all P prompts are resident, ``slots`` of them are in flight; a slot
+        whose trajectory ends takes the next ticket on the device.  ``ticket`` (int32 device tensor of one element, zeroed by
+        its owner) may be shared between GPUs, which then split one prompt list between them.  Returns device tensors:
+        latents (P, C, h, w), steps (P,) (0 for prompts another GPU processed), sigmas (P, max_steps + 1)."""
+        lib = L.load()
+        P, Cc, h, w = latents.shape
+        dev, f32 = self.device, torch.float32
+        if not 1 <= slots <= P:
+            raise ValueError(f"slots must be in [1, {P}]")
+        plan = self.plan(slots, True, h, prompt_embeds.shape[1], max_inference_steps)
+        cvt = lambda t: t.to(device=dev, dtype=f32).contiguous()
+        lat, pe, ne, pp, npp = cvt(latents), cvt(prompt_embeds), cvt(negative_prompt_embeds), cvt(pooled_prompt_embeds), cvt(negative_pooled_prompt_embeds)
+        if ticket is None:
+            ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        out_lat = torch.zeros(P, Cc, h, w, device=dev, dtype=f32) if out_latents is None else out_latents
+        out_steps = torch.zeros(P, dtype=torch.int32, device=dev)
+        out_sig = torch.zeros(P, max_inference_steps + 1, device=dev, dtype=f32)
+        nbytes = lib.tpdm_queue_workspace_bytes(plan.handle, P)
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
+        base = (ws.data_ptr() + 1023) // 1024 * 1024
+        active_host = torch.ones(4096, dtype=torch.int32).pin_memory()
+        with torch.cuda.device(dev):
+            stream = L.stream_ptr()
+            L.check(lib.tpdm_queue_begin(plan.handle, P, L.ptr(lat), L.ptr(ne), L.ptr(pe), L.ptr(npp), L.ptr(pp), float(guidance_scale), base,
+                                         nbytes, ticket.data_ptr(), L.ptr(out_lat), L.ptr(out_steps), L.ptr(out_sig), stream))
+            act_p, slot_p = L.vp(), L.vp()
+            L.check(lib.tpdm_queue_status(plan.handle, C.byref(act_p), C.byref(slot_p)))
+            off = act_p.value - ws.data_ptr()          # the counters live in the queue workspace
+            active = ws[off: off + 4].view(torch.int32)
+            events = []
+            limit = (P + slots - 1) // slots * max_inference_steps + 2 * max_inference_steps
+            steps_run = 0
+            for it in range(min(limit, active_host.numel())):
+                L.check(lib.tpdm_queue_step(plan.handle, stream))
+                steps_run += 1
+                active_host[it: it + 1].copy_(active, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                events.append(ev)
+                if it >= 1:                      # look at the flag one step late: the device never waits for the host
+                    events[it - 1].synchronize()
+                    if int(active_host[it - 1]) == 0:
+                        break
+            torch.cuda.current_stream().synchronize()
+        self._queue_keepalive = (ws, lat, pe, ne, pp, npp, ticket)
+        return dict(latents=out_lat, steps=out_steps, sigmas=out_sig, device_steps=steps_run)

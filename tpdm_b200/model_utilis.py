@@ -32,6 +32,8 @@ class CustomDiffusionModelOutput(BaseOutput):
     logprobs: torch.Tensor
     prob_masks: torch.Tensor
     latents: Optional[torch.Tensor] = None  # tpdm_b200 addition: final (last valid) latents, (B, C, h, w)
+    steps: Optional[torch.Tensor] = None    # sample_queue: denoising steps each prompt took (0: processed by another GPU)
+    device_steps: Optional[int] = None      # sample_queue: steps this GPU executed
 
 
 class CustomFlowMatchEulerDiscreteScheduler:

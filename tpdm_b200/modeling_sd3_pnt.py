@@ -320,6 +320,32 @@ class SD3PredictNextTimeStepModel(nn.Module):
 
     # ---------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
+    def sample_queue(self, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds, latents=None,
+                     slots: int = 2, max_inference_steps: int = 28, guidance_scale: float = 7.0, generator=None, ticket=None,
+                     decode: bool = False, output_type: str = "pil"):
+        """Many prompts with different trajectory lengths on one GPU (BASELINE config 3): ``slots`` prompts are in flight, a
+        finished one is replaced on the device from a ticket counter (which several GPUs may share).  Each prompt follows
+        exactly the trajectory ``forward(..., predict=True)`` gives it with batch size 1.  Returns a
+        CustomDiffusionModelOutput with ``latents`` (P, C, h, w), ``steps`` (P,), ``sigmas`` (P, max_steps + 1) and, with
+        ``decode=True`` and a VAE, ``images``."""
+        P = prompt_embeds.shape[0]
+        side = self.default_sample_size * self.vae_scale_factor
+        if latents is None:
+            latents = self.prepare_latents(P, self.transformer.config.in_channels, side, side, prompt_embeds.dtype, self.device, generator, None)
+        res = self.get_engine().sample_queue(latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
+                                             negative_pooled_prompt_embeds, int(slots), int(max_inference_steps), float(guidance_scale),
+                                             ticket=ticket)
+        images = []
+        if decode and self.vae is not None and hasattr(self.vae, "decode_latents"):
+            mine = (res["steps"] > 0).nonzero().flatten().tolist()
+            images = {i: self.vae.decode_latents(res["latents"][i: i + 1], output_type) for i in mine}
+        return CustomDiffusionModelOutput(
+            init_noise_latents=latents, hidden_states_combineds=None, tembs=None, images=images, last_valid_indices=[], alphas=None,
+            betas=None, sigmas=res["sigmas"], logprobs=None, prob_masks=None, latents=res["latents"], steps=res["steps"],
+            device_steps=res["device_steps"])
+
+    # ---------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
     def only_predict_logprobs(self, fix_sigmas: torch.Tensor, fix_hidden_states_combineds: torch.Tensor, fix_tembs: torch.Tensor):
         """modeling_sd3_pnt.py:670-726 (forward replay; gradients w.r.t. the TPM are the next row of SURVEY section 8a)."""
         if fix_sigmas is None:

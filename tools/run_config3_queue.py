@@ -55,6 +55,49 @@ def main():
         busy[0] += dt
         return {"steps": int(out.sigmas.shape[1]), "rank": rank, "seconds": dt}
 
+    if "--device-queue" in sys.argv:
+        # every GPU holds all prompts and drains ONE ticket counter (CUDA IPC, system-scope atomics) with `slots` prompts in flight
+        from tpdm_b200.work_queue import SharedTicket
+
+        slots = int(sys.argv[sys.argv.index("--slots") + 1]) if "--slots" in sys.argv else 2
+        allin = [inputs(i) for i in range(n_prompts)]
+        cat = {k: torch.cat([a[k] for a in allin]) for k in allin[0]}
+        del allin
+        ticket = SharedTicket.create()
+        model.sample_queue(cat["prompt_embeds"][:slots], cat["negative_prompt_embeds"][:slots], cat["pooled_prompt_embeds"][:slots],
+                           cat["negative_pooled_prompt_embeds"][:slots], latents=cat["latents"][:slots], slots=slots, max_inference_steps=28)
+        ticket.reset()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = model.sample_queue(cat["prompt_embeds"], cat["negative_prompt_embeds"], cat["pooled_prompt_embeds"],
+                                 cat["negative_pooled_prompt_embeds"], latents=cat["latents"], slots=slots, max_inference_steps=28, ticket=ticket)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        makespan = max_over_ranks(wall, dev)
+        steps = out.steps.clone()
+        if world > 1:
+            dist.all_reduce(steps)                 # each prompt was processed by exactly one rank
+            counts = [torch.zeros_like(out.steps) for _ in range(world)]
+            dist.all_gather(counts, (out.steps > 0).int())
+            per_rank = [int(c.sum()) for c in counts]
+            dsteps = [None] * world
+            dist.all_gather_object(dsteps, out.device_steps)
+        else:
+            per_rank, dsteps = [int((out.steps > 0).sum())], [out.device_steps]
+        if rank == 0:
+            st = steps.tolist()
+            assert all(s > 0 for s in st), "a prompt was not processed"
+            assert sum(per_rank) == n_prompts, "a prompt was processed twice"
+            hist = {}
+            for s_ in st:
+                hist[s_] = hist.get(s_, 0) + 1
+            print(json.dumps({"config": f"SD3-medium 1024^2, {n_prompts} prompts, device-side queue, {slots} slots per GPU, shared ticket",
+                              "n_gpus": world, "makespan_s": makespan, "images_per_s": n_prompts / makespan, "prompts_per_gpu": per_rank,
+                              "device_steps_per_gpu": dsteps, "total_steps": sum(st), "steps_histogram": dict(sorted(hist.items())),
+                              "ideal_device_steps": sum(st) / (world * slots)}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

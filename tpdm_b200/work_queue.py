@@ -71,3 +71,69 @@ def max_over_ranks(value: float, device: Optional[torch.device] = None) -> float
     t = torch.tensor([value], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class SharedTicket:
+    """One int32 ticket counter in the memory of local rank 0's GPU, mapped into every process of the box through CUDA IPC.
+    `tpdm_queue_*` claims prompts from it with system-scope atomics over NVLink, so the GPUs of one node drain a single
+    prompt list with no host round trip and no collective.  Usage (all ranks, same order):
+        ticket = SharedTicket.create()        # collective: broadcasts the IPC handle through torch.distributed
+        model.sample_queue(..., ticket=ticket)
+    Needs peer access between the GPUs (NVLink / NVSwitch boxes); with world size 1 it is a plain device counter."""
+
+    def __init__(self, ptr: int, owner: bool, opened=None):
+        self._ptr, self._owner, self._opened = ptr, owner, opened
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    @classmethod
+    def create(cls, group=None) -> "SharedTicket":
+        from cuda.bindings import runtime as rt
+
+        def ok(res):
+            err, *rest = res
+            if int(err) != 0:
+                raise RuntimeError(f"CUDA runtime error {err} while setting up the shared ticket")
+            return rest[0] if len(rest) == 1 else rest
+
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        rank = dist.get_rank(group) if multi else 0
+        if rank == 0:
+            ptr = ok(rt.cudaMalloc(4))
+            ok(rt.cudaMemset(ptr, 0, 4))
+            ok(rt.cudaDeviceSynchronize())
+            handle = bytes(ok(rt.cudaIpcGetMemHandle(ptr)).reserved) if multi else b""
+        else:
+            ptr, handle = 0, b""
+        if not multi:
+            return cls(int(ptr), True)
+        box = [handle]
+        dist.broadcast_object_list(box, src=0, group=group)
+        if rank == 0:
+            out = cls(int(ptr), True)
+        else:
+            h = rt.cudaIpcMemHandle_t()
+            h.reserved = box[0]
+            remote = ok(rt.cudaIpcOpenMemHandle(h, rt.cudaIpcMemLazyEnablePeerAccess))
+            out = cls(int(remote), False, opened=remote)
+        dist.barrier(group)
+        return out
+
+    def reset(self, group=None) -> None:
+        """collective: the owner zeroes the counter, everybody waits"""
+        from cuda.bindings import runtime as rt
+
+        if self._owner:
+            rt.cudaMemset(self._ptr, 0, 4)
+            rt.cudaDeviceSynchronize()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.barrier(group)
+
+    def value(self) -> int:
+        from cuda.bindings import runtime as rt
+        import numpy as np
+
+        buf = np.zeros(1, dtype=np.int32)
+        rt.cudaMemcpy(buf.ctypes.data, self._ptr, 4, rt.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+        return int(buf[0])

@@ -8,17 +8,18 @@
 //
 // One CTA = one 128-row query tile of one (batch, head); 256 threads; two CTAs co-resident per SM (dp = 64).
 //   warp 0      TMA producer  (Q once, K/V tiles of 128 keys through a 2-stage smem ring)
-//   warp 1      MMA issuer.  Keys are consumed in HALF-tiles of 64:  S[b] = Q K_half^T (SS, 128x64xdp) and
-//               O += P[b] V_half (A = P from TMEM, B = V MN-major from smem), b = half-tile parity
+//   warp 1      MMA issuer for S.  Keys are consumed in HALF-tiles of 64:  S[b] = Q K_half^T (SS, 128x64xdp), b = parity
+//   warp 3      MMA issuer for O += P[b] V_half (A = P from TMEM, B = V MN-major from smem)
 //   warp 2      TMEM allocator
 //   warps 4-7   softmax, one thread per query row.
 // S and P are DOUBLE-BUFFERED in TMEM (S[2] 64 fp32 columns each, P[2] 32 packed-bf16 columns each, O dp columns), so the
-// softmax warps never wait for the tensor core in steady state: while they work on half-tile i the MMA warp has already
-// produced S(i+1) and is accumulating P(i-1) V.  The kernel is then bound by the MUFU ex2 rate, which is the d=64 limit.
-// Softmax: fp32, exp2 with log2(e)/sqrt(d) folded into one FFMA2, single pass per half-tile against a possibly stale
-// running max (exact: the final 1/l normalisation cancels it); when a half-tile raises the max by more than 2^8 the
-// accumulator O and the row sum are rescaled once the outstanding P V has drained; the first half-tile, the masked tail
-// and (never observed) jumps above 2^100 take an exact two-pass route.
+// softmax warps never wait for the tensor core in steady state: while they work on half-tile i the MMA warps have already
+// produced S(i+1) and are accumulating P(i-1) V.
+// Softmax: fp32, exp2 with log2(e)/sqrt(d) folded into one FFMA2, ONE pass per half-tile against a reference max that is
+// fixed by the first half-tile and not tracked afterwards: fp32 sums and bf16 P carry 8 exponent bits, so the result stays
+// exact (the final 1/l cancels the reference) until a row grows past 2^128 relative to it.  That is detected from the row
+// sum before P is published; such a half-tile, the first one and the masked tail take an exact two-pass route that moves
+// the reference and rescales O and l once the outstanding P V has drained.
 //
 // Where the time goes (ncu source-level samples, profiles/r01_attention_ncu.txt): per 64-key half-tile and CTA the kernel
 // needs 512 cycles of the MUFU pipe (ex2, 16 / clk / SM) AND 512 cycles of the TMEM read port (S in fp32, 64 B / clk / SM)

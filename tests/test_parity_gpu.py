@@ -505,3 +505,30 @@ def test_device_prompt_queue_matches_per_prompt_sampling():
     assert b.steps.tolist() == [0, 0, 0, 0] + ref_steps[4:]
     with pytest.raises(ValueError):
         model.sample_queue(pe, ne, pp, npp, latents=lat, slots=P + 1, max_inference_steps=T)
+
+
+def test_mmdit_sd35_large_width_vs_oracle():
+    """SD3.5-large block shape (38 heads x 64 = 2432 wide, QK-RMSNorm): hidden sizes that are not multiples of the 256-wide
+    GEMM tile (N tails in every projection) and take the generic LayerNorm path; 2 layers, 512^2."""
+    from oracle import sd3_oracle as O
+    from tpdm_b200.transformer_sd3 import CustomSD3Transformer2DModel
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = O.SD3Config(sample_size=64, num_layers=2, attention_head_dim=64, num_attention_heads=38, caption_projection_dim=2432,
+                      pos_embed_max_size=192, qk_norm="rms_norm")
+    torch.manual_seed(77)
+    ora = O.OracleSD3Transformer(cfg).requires_grad_(False).eval().to("cuda")
+    model = CustomSD3Transformer2DModel(sample_size=64, num_layers=2, attention_head_dim=64, num_attention_heads=38, caption_projection_dim=2432,
+                                        pos_embed_max_size=192, qk_norm="rms_norm", device="cuda", dtype=torch.bfloat16)
+    model.load_state_dict(ora.state_dict())
+    ora.load_state_dict(model.state_dict())
+    g = torch.Generator(device="cuda").manual_seed(8)
+    lat = torch.randn(2, 16, 64, 64, device="cuda", generator=g)
+    enc = torch.randn(2, 333, 4096, device="cuda", generator=g)
+    pooled = torch.randn(2, 2048, device="cuda", generator=g)
+    ts = torch.tensor([100.0, 900.0], device="cuda")
+    with torch.no_grad():
+        rv, rt, rh1, rh2 = ora(lat, enc, pooled, ts)
+    v, temb, h1, h2 = model(lat, enc, pooled, ts, return_dict=False)
+    assert rel(temb, rt) < 2e-3 and rel(h1, rh1) < 1e-3 and rel(h2, rh2) < VEL_TOL and rel(v, rv) < VEL_TOL

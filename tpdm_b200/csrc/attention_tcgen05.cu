@@ -29,6 +29,8 @@
 // stand-alone, 3 % slower in the trajectory), prefetching the next half-tile's first 32 S columns during the second
 // exponential block (398 us: 128 registers and spills), a second MMA-issuing warp for P V (kept, +2 %).  With the
 // exponentials compiled out the kernel still takes 260 us, so MUFU and the TMEM-read side are about equally loaded.
+// Not tried: fp16 accumulators for S (half the TMEM read) -- the error it adds grows with the logit magnitude and cannot
+// be checked against real checkpoints offline (random-init weights give near-uniform attention).
 #include <cuda_bf16.h>
 
 #include "common.cuh"

@@ -250,6 +250,8 @@ int tpdm_queue_begin(tpdm_plan* plan, int n_prompts, const float* latents_all, c
                      float* out_latents, int* out_steps, float* out_sigmas, void* stream);
 /* one denoising step of every occupied slot, then retire / refill.  No host synchronisation. */
 int tpdm_queue_step(tpdm_plan* plan, void* stream);
+/* the same step replayed from a CUDA graph captured on the first call (stream must not be the legacy default stream) */
+int tpdm_queue_step_graph(tpdm_plan* plan, void* stream);
 /* device pointers: *active_slots -> int, slots holding a prompt after the last enqueued step (0 = drained);
  * *slot_prompts -> int[batch] */
 int tpdm_queue_status(tpdm_plan* plan, const int** active_slots, const int** slot_prompts);

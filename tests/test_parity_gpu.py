@@ -487,7 +487,9 @@ def test_device_prompt_queue_matches_per_prompt_sampling():
         ref_lat.append(o.latents[0])
         ref_sig.append(o.sigmas[0])
     assert len(set(ref_steps)) > 1, ref_steps          # the stress is real: lengths differ
-    q = model.sample_queue(pe, ne, pp, npp, latents=lat, slots=3, max_inference_steps=T)
+    q = model.sample_queue(pe, ne, pp, npp, latents=lat, slots=3, max_inference_steps=T)     # CUDA-graph replay of the step
+    q_eager = model.sample_queue(pe, ne, pp, npp, latents=lat, slots=3, max_inference_steps=T, use_graph=False)
+    assert q_eager.steps.tolist() == ref_steps and rel(q_eager.latents, q.latents) < 1e-6
     assert q.steps.tolist() == ref_steps
     for i in range(P):
         n = ref_steps[i]

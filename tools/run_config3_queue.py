@@ -70,7 +70,8 @@ def main():
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         out = model.sample_queue(cat["prompt_embeds"], cat["negative_prompt_embeds"], cat["pooled_prompt_embeds"],
-                                 cat["negative_pooled_prompt_embeds"], latents=cat["latents"], slots=slots, max_inference_steps=28, ticket=ticket)
+                                 cat["negative_pooled_prompt_embeds"], latents=cat["latents"], slots=slots, max_inference_steps=28, ticket=ticket,
+                                 use_graph="--no-graph" not in sys.argv)
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         makespan = max_over_ranks(wall, dev)

@@ -77,7 +77,12 @@ struct tpdm_plan {
     float *ctx0_all = nullptr, *text_all = nullptr, *sigma_cur = nullptr, *sigma_next = nullptr, *out_latents = nullptr, *out_sigmas = nullptr;
     int *slot_prompt = nullptr, *slot_step = nullptr, *slot_flush = nullptr, *slot_load = nullptr, *ticket = nullptr, *out_steps = nullptr,
         *active = nullptr, *idle_flag = nullptr;
+    cudaGraphExec_t graph = nullptr;   // one captured queue step (every pointer of a queue step is fixed between steps)
+    long long graph_launches = 0;
   } q;
+  ~tpdm_plan() {
+    if (q.graph) cudaGraphExecDestroy(q.graph);
+  }
 };
 
 namespace {
@@ -613,6 +618,10 @@ int tpdm_queue_begin(tpdm_plan* p, int n_prompts, const float* latents_all, cons
   const int B = p->B, D = ctx->D, T = p->T, J = ctx->cfg.joint_attention_dim, PD = ctx->cfg.pooled_projection_dim;
   const size_t nctx = static_cast<size_t>(T) * D;
   tpdm_plan::Queue& q = p->q;
+  if (q.graph) {
+    cudaGraphExecDestroy(q.graph);
+    q.graph = nullptr;
+  }
   Carver c(queue_workspace);
   q.ctx0_all = c.take<float>(static_cast<size_t>(n_prompts) * 2 * nctx);
   q.text_all = c.take<float>(static_cast<size_t>(n_prompts) * 2 * D);
@@ -672,6 +681,33 @@ int tpdm_queue_step(tpdm_plan* p, void* stream) {
                         p->q.sigma_next, 1, nullptr, s));
   TPDM_TRY(k_queue_advance(queue_args(p, 0), s));
   TPDM_TRY(queue_move(p, s));
+  return 0;
+}
+
+int tpdm_queue_step_graph(tpdm_plan* p, void* stream) {
+  TPDM_CHECK(p, TPDM_ERR_ARG, "tpdm_queue_step_graph: null plan");
+  TPDM_CHECK(p->q.begun, TPDM_ERR_STATE, "tpdm_queue_step_graph: call tpdm_queue_begin first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->q.graph == nullptr) {
+    // a queue step has no host-side argument that changes between steps: capture it once, replay it every step
+    const long long before = launches_so_far();
+    cudaGraph_t g = nullptr;
+    TPDM_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int st = tpdm_queue_step(p, s);
+    const cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (st != 0) {
+      if (g) cudaGraphDestroy(g);
+      return st;
+    }
+    TPDM_CHECK(e == cudaSuccess && g != nullptr, TPDM_ERR_CUDA, "tpdm_queue_step_graph: stream capture failed: %s", cudaGetErrorString(e));
+    const cudaError_t ei = cudaGraphInstantiate(&p->q.graph, g, 0);
+    cudaGraphDestroy(g);
+    TPDM_CHECK(ei == cudaSuccess, TPDM_ERR_CUDA, "tpdm_queue_step_graph: cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+    p->q.graph_launches = launches_so_far() - before;
+    count_launches(-p->q.graph_launches);  // the capture itself launched nothing
+  }
+  TPDM_CUDA_OK(cudaGraphLaunch(p->q.graph, s));
+  count_launches(p->q.graph_launches);
   return 0;
 }
 

@@ -38,6 +38,8 @@ int num_sms();
 
 // launch accounting + optional CUDA-event brackets per kernel class (bench.py roofline); class 0 = GEMM, 1 = attention
 void count_launch();
+void count_launches(long long n);  // kernels replayed through a CUDA graph
+long long launches_so_far();
 void prof_begin(int cls, double flops, cudaStream_t s);
 void prof_end(cudaStream_t s);
 

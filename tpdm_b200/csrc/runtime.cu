@@ -37,6 +37,8 @@ bool pdl_enabled() {
   return on;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
 
 namespace {
 struct Profiler {

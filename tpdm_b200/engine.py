@@ -370,7 +370,7 @@ class Engine:
 
     def sample_queue(self, latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
                      slots: int, max_inference_steps: int, guidance_scale: float, ticket: Optional[torch.Tensor] = None,
-                     out_latents: Optional[torch.Tensor] = None):
+                     out_latents: Optional[torch.Tensor] = None, use_graph: bool = True):
         """Device-side prompt queue (``tpdm_queue_*``): all P prompts are resident, ``slots`` of them are in flight; a slot
         whose trajectory ends takes the next ticket on the device.  ``ticket`` (int32 device tensor of one element, zeroed by
         its owner) may be shared between GPUs, which then split one prompt list between them.  Returns device tensors:
@@ -392,7 +392,13 @@ class Engine:
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
         base = (ws.data_ptr() + 1023) // 1024 * 1024
         active_host = torch.ones(4096, dtype=torch.int32).pin_memory()
-        with torch.cuda.device(dev):
+        # the step is replayed from a CUDA graph (captured on the first step), which needs a non-default stream
+        qs = getattr(self, "_queue_stream", None)
+        if qs is None:
+            qs = self._queue_stream = torch.cuda.Stream(device=dev)
+        qs.wait_stream(torch.cuda.current_stream(dev))
+        step_fn = lib.tpdm_queue_step_graph if use_graph else lib.tpdm_queue_step
+        with torch.cuda.device(dev), torch.cuda.stream(qs):
             stream = L.stream_ptr()
             L.check(lib.tpdm_queue_begin(plan.handle, P, L.ptr(lat), L.ptr(ne), L.ptr(pe), L.ptr(npp), L.ptr(pp), float(guidance_scale), base,
                                          nbytes, ticket.data_ptr(), L.ptr(out_lat), L.ptr(out_steps), L.ptr(out_sig), stream))
@@ -404,7 +410,7 @@ class Engine:
             limit = (P + slots - 1) // slots * max_inference_steps + 2 * max_inference_steps
             steps_run = 0
             for it in range(min(limit, active_host.numel())):
-                L.check(lib.tpdm_queue_step(plan.handle, stream))
+                L.check(step_fn(plan.handle, stream))
                 steps_run += 1
                 active_host[it: it + 1].copy_(active, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -415,5 +421,6 @@ class Engine:
                     if int(active_host[it - 1]) == 0:
                         break
             torch.cuda.current_stream().synchronize()
+        torch.cuda.current_stream(dev).wait_stream(qs)
         self._queue_keepalive = (ws, lat, pe, ne, pp, npp, ticket)
         return dict(latents=out_lat, steps=out_steps, sigmas=out_sig, device_steps=steps_run)

@@ -322,7 +322,7 @@ class SD3PredictNextTimeStepModel(nn.Module):
     @torch.no_grad()
     def sample_queue(self, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds, latents=None,
                      slots: int = 2, max_inference_steps: int = 28, guidance_scale: float = 7.0, generator=None, ticket=None,
-                     decode: bool = False, output_type: str = "pil"):
+                     decode: bool = False, output_type: str = "pil", use_graph: bool = True):
         """Many prompts with different trajectory lengths on one GPU (BASELINE config 3): ``slots`` prompts are in flight, a
         finished one is replaced on the device from a ticket counter (which several GPUs may share).  Each prompt follows
         exactly the trajectory ``forward(..., predict=True)`` gives it with batch size 1.  Returns a
@@ -334,7 +334,7 @@ class SD3PredictNextTimeStepModel(nn.Module):
             latents = self.prepare_latents(P, self.transformer.config.in_channels, side, side, prompt_embeds.dtype, self.device, generator, None)
         res = self.get_engine().sample_queue(latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
                                              negative_pooled_prompt_embeds, int(slots), int(max_inference_steps), float(guidance_scale),
-                                             ticket=ticket)
+                                             ticket=ticket, use_graph=use_graph)
         images = []
         if decode and self.vae is not None and hasattr(self.vae, "decode_latents"):
             mine = (res["steps"] > 0).nonzero().flatten().tolist()

@@ -44,6 +44,10 @@ def peaks():
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback")
 
 
+def pk_hbm() -> float:
+    return float(peaks()["hbm"])
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -174,8 +178,8 @@ def run_ours(args, rank, world, local_rank):
     p1.record()
     torch.cuda.synchronize()
     ms_prof = p0.elapsed_time(p1)
-    pms, pfl, pct = (C.c_double * 2)(), (C.c_double * 2)(), (C.c_longlong * 2)()
-    L.check(lib.tpdm_profile_stop(pms, pfl, pct, 2))
+    pms, pfl, pct = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_longlong * 4)()
+    L.check(lib.tpdm_profile_stop(pms, pfl, pct, 4))
 
     # ---- timed region 2: host buffers through the public API ("e2e") --------------------------------------------
     h2d = sum(v.numel() * v.element_size() for v in host[0].values())
@@ -221,6 +225,13 @@ def run_ours(args, rank, world, local_rank):
             kernels[name] = dict(ms_total=pms[idx], launches=int(pct[idx]), tflops=pfl[idx] / pms[idx] / 1e9,
                                  share_of_trajectory=pms[idx] / ms_prof)
     dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
+    # the two largest bandwidth kernels of the step, against the measured HBM rate (class "flops" = algorithmic bytes)
+    hbm = {}
+    for idx, name in ((2, "ln_modulate"), (3, "adaln_gemv_bf16")):
+        if pct[idx]:
+            gbs = pfl[idx] / pms[idx] / 1e6
+            hbm[name] = dict(ms_total=pms[idx], launches=int(pct[idx]), gb_per_s=gbs, frac_of_hbm_peak=gbs / pk_hbm(),
+                             share_of_trajectory=pms[idx] / ms_prof)
     roofline = None
     if dom:
         roofline = dict(bound="tensor", kernel=dom, achieved=kernels[dom]["tflops"], peak=pk["tflops"], unit="TFLOP/s",
@@ -229,7 +240,7 @@ def run_ours(args, rank, world, local_rank):
                                        "ncu --set full (GEMM: mean of the four per-block shapes)",
                         peak_source=pk["source"] + " (sustained bf16)",
                         sampled_over="one extra trajectory with per-launch CUDA events, right after the timed region",
-                        kernels=kernels)
+                        kernels=kernels, hbm_kernels=hbm)
     steps_per_image = n_denoise / K
     step_tflops = mmdit_flops_1024() * n_denoise / (ms_value / 1e3) / 1e12
     line = {

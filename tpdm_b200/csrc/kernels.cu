@@ -842,7 +842,10 @@ int k_gemv_f32(const float* W, const float* bias, const float* x, int ldx, const
 }
 int k_gemv_bf16(const bf16* W, const float* bias, const float* x, int ldx, const float* addend, float* y, int ldy, int Bt, int J, int K,
                 int act, cudaStream_t s) {
-  return gemv_launch<bf16>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act, s);
+  prof_begin(3, 2.0 * J * K, s);  // profile class 3: the weight matrix is read once
+  const int st = gemv_launch<bf16>(W, bias, x, ldx, addend, y, ldy, Bt, J, K, act, s);
+  prof_end(s);
+  return st;
 }
 
 int k_patchify(const float* latents, const float* Wp, const float* bias, const float* pos_table, int pos_max, float* x, int Bl, int dup,
@@ -874,12 +877,16 @@ int k_ln_modulate(const LnSeg* segs, int nseg, int D, cudaStream_t s) {
   const unsigned grid = static_cast<unsigned>(P.blocks_total);
   const size_t smem = static_cast<size_t>(2) * D * sizeof(float);
   TPDM_CHECK(smem <= 48 * 1024, TPDM_ERR_SHAPE, "ln_modulate: D=%d too large", D);
+  double bytes = 0;  // profile class 2: algorithmic bytes = one fp32 read + one bf16 write per element
+  for (int i = 0; i < nseg; ++i) bytes += 6.0 * segs[i].batch * segs[i].rows * D;
+  prof_begin(2, bytes, s);
   if (D == 1536)
     TPDM_CUDA_OK(launch_pdl(ln_modulate_kernel<12>, dim3(grid), dim3(256), smem, s, P));
   else if (D == 384)
     TPDM_CUDA_OK(launch_pdl(ln_modulate_kernel<3>, dim3(grid), dim3(256), smem, s, P));
   else
     TPDM_CUDA_OK(launch_pdl(ln_modulate_kernel<0>, dim3(grid), dim3(256), smem, s, P));
+  prof_end(s);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

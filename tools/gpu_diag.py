@@ -146,6 +146,51 @@ if __name__ == "__main__":
         flops = 10.472e12 * (side / 128) ** 2 if side == 128 else float("nan")
         print(f"vae decode {side*8}^2: {ms:.2f} ms  ({flops/ms/1e9:.0f} TFLOP/s algorithmic); GEMM-class kernels {pms[0]:.2f} ms over {pct[0]} launches "
               f"({pfl[0]/pms[0]/1e9:.0f} TFLOP/s), everything else {ms - pms[0]:.2f} ms; workspace {vae._workspace.numel()/2**30:.2f} GiB", flush=True)
+    if which == "gemm_sustained":   # 4 s back to back: our FF1 GEMM vs torch.matmul (cuBLAS) on the same shape, with clocks
+        import subprocess, threading
+        rows, N, K = 8858, 6144, 1536
+        A = (torch.randn(rows, K, device=dev) * 0.5).bfloat16()
+        W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
+        bias = torch.zeros(N, device=dev)
+        out = torch.empty(rows, N, device=dev, dtype=torch.bfloat16)
+        def ours():
+            lib.tpdm_gemm_bf16(L.ptr(A), L.ptr(W), L.ptr(bias), None, L.ptr(out), 1, rows, N, K, 0, None)
+        def cublas():
+            torch.matmul(A, W.t(), out=out)
+        for name, fn in (("tpdm gemm2", ours), ("torch.matmul", cublas), ("tpdm gemm2", ours), ("torch.matmul", cublas)):
+            clocks = []
+            stop = [False]
+            def sample():
+                while not stop[0]:
+                    r = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits"], capture_output=True, text=True)
+                    try:
+                        c, pw = r.stdout.strip().split(",")
+                        clocks.append((float(c), float(pw)))
+                    except Exception:
+                        pass
+                    time.sleep(0.2)
+            th = threading.Thread(target=sample, daemon=True)
+            for _ in range(20):
+                fn()
+            torch.cuda.synchronize()
+            th.start()
+            n, t0 = 0, time.perf_counter()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            while time.perf_counter() - t0 < 4.0:
+                for _ in range(200):
+                    fn()
+                n += 200
+                torch.cuda.synchronize()
+            e1.record()
+            torch.cuda.synchronize()
+            stop[0] = True
+            th.join()
+            ms = e0.elapsed_time(e1)
+            late = clocks[len(clocks) // 2:]
+            mhz = sorted(c for c, _ in late)[len(late) // 2] if late else float("nan")
+            pw = max((p for _, p in late), default=float("nan"))
+            print(f"{name:13s} {rows}x{N}x{K}: {2.0*rows*N*K*n/ms/1e9:7.1f} TFLOP/s sustained over {ms/1e3:.1f} s, median SM clock {mhz:.0f} MHz, max power {pw:.0f} W", flush=True)
     if which == "ln":
         for (batch, rows) in ((2, 4096), (2, 333)):
             D = 1536

@@ -148,7 +148,7 @@ if __name__ == "__main__":
               f"({pfl[0]/pms[0]/1e9:.0f} TFLOP/s), everything else {ms - pms[0]:.2f} ms; workspace {vae._workspace.numel()/2**30:.2f} GiB", flush=True)
     if which == "gemm_sustained":   # 4 s back to back: our FF1 GEMM vs torch.matmul (cuBLAS) on the same shape, with clocks
         import subprocess, threading
-        rows, N, K = 8858, 6144, 1536
+        rows, N, K = (int(v) for v in sys.argv[2:5]) if len(sys.argv) >= 5 else (8858, 6144, 1536)
         A = (torch.randn(rows, K, device=dev) * 0.5).bfloat16()
         W = (torch.randn(N, K, device=dev) * 0.05).bfloat16()
         bias = torch.zeros(N, device=dev)

@@ -75,8 +75,8 @@ struct tpdm_plan {
     int n_prompts = 0, begun = 0;
     const float* noise_all = nullptr;
     float *ctx0_all = nullptr, *text_all = nullptr, *sigma_cur = nullptr, *sigma_next = nullptr, *out_latents = nullptr, *out_sigmas = nullptr;
-    int *slot_prompt = nullptr, *slot_step = nullptr, *slot_flush = nullptr, *slot_load = nullptr, *ticket = nullptr, *out_steps = nullptr,
-        *active = nullptr, *idle_flag = nullptr;
+    int *slot_prompt = nullptr, *slot_step = nullptr, *slot_flush = nullptr, *slot_load = nullptr, *slot_active = nullptr, *ticket = nullptr,
+        *out_steps = nullptr, *active = nullptr, *idle_flag = nullptr;
     cudaGraphExec_t graph = nullptr;   // one captured queue step (every pointer of a queue step is fixed between steps)
     long long graph_launches = 0;
   } q;
@@ -561,7 +561,7 @@ size_t queue_bytes(const tpdm_plan* p, int n_prompts) {
   c.take<float>(static_cast<size_t>(n_prompts) * 2 * ctx);
   c.take<float>(static_cast<size_t>(n_prompts) * 2 * D);
   c.take<float>(2 * B);
-  c.take<int>(4 * B + 8);
+  c.take<int>(5 * B + 8);
   return c.off + 1024;
 }
 QueueArgs queue_args(const tpdm_plan* p, int init) {
@@ -574,6 +574,7 @@ QueueArgs queue_args(const tpdm_plan* p, int init) {
   a.slot_step = q.slot_step;
   a.slot_flush = q.slot_flush;
   a.slot_load = q.slot_load;
+  a.slot_active = q.slot_active;
   a.ticket = q.ticket;
   a.out_steps = q.out_steps;
   a.out_sigmas = q.out_sigmas;
@@ -627,11 +628,12 @@ int tpdm_queue_begin(tpdm_plan* p, int n_prompts, const float* latents_all, cons
   q.text_all = c.take<float>(static_cast<size_t>(n_prompts) * 2 * D);
   q.sigma_cur = c.take<float>(2 * B);
   q.sigma_next = q.sigma_cur + B;
-  q.slot_prompt = c.take<int>(4 * B + 8);
+  q.slot_prompt = c.take<int>(5 * B + 8);
   q.slot_step = q.slot_prompt + B;
   q.slot_flush = q.slot_step + B;
   q.slot_load = q.slot_flush + B;
-  q.active = q.slot_load + B;
+  q.slot_active = q.slot_load + B;
+  q.active = q.slot_active + B;
   q.idle_flag = q.active + 1;
   q.n_prompts = n_prompts;
   q.noise_all = latents_all;
@@ -655,7 +657,7 @@ int tpdm_queue_begin(tpdm_plan* p, int n_prompts, const float* latents_all, cons
       }
   }
   TPDM_CUDA_OK(cudaMemsetAsync(q.slot_prompt, 0xff, sizeof(int) * B, s));  // -1: every slot is idle and asks for a ticket
-  TPDM_CUDA_OK(cudaMemsetAsync(q.slot_step, 0, sizeof(int) * (3 * B + 8), s));
+  TPDM_CUDA_OK(cudaMemsetAsync(q.slot_step, 0, sizeof(int) * (4 * B + 8), s));
   TPDM_TRY(k_queue_advance(queue_args(p, 1), s));
   TPDM_TRY(queue_move(p, s));
   q.begun = 1;
@@ -671,11 +673,14 @@ int tpdm_queue_step(tpdm_plan* p, void* stream) {
   const int B = p->B;
   // a step enqueued after the queue drained (idle_flag set) turns into empty launches
   set_skip_flag(p->q.idle_flag);
+  // emptied slots (the tail of the queue) are skipped tile by tile / CTA by CTA inside the heavy kernels
+  if (B > 1) set_batch_mask(p->q.slot_active, B);
   int st_mm = run_mmdit(p, p->latents, B, 2, p->q.sigma_cur, 1, 1000.0f, 2, nullptr, nullptr, true, s);
   set_skip_flag(nullptr);
+  if (st_mm == 0) st_mm = k_cfg_combine(p->temb, p->temb_cfg, nullptr, B, ctx->D, p->guidance, s);
+  if (st_mm == 0) st_mm = run_tpm(p, B, p->temb_cfg, p->alpha_beta, s);
+  set_batch_mask(nullptr, 1);
   TPDM_TRY(st_mm);
-  TPDM_TRY(k_cfg_combine(p->temb, p->temb_cfg, nullptr, B, ctx->D, p->guidance, s));
-  TPDM_TRY(run_tpm(p, B, p->temb_cfg, p->alpha_beta, s));
   TPDM_TRY(k_queue_schedule(queue_args(p, 0), s));
   TPDM_TRY(k_unpatchify(p->pout, B, 1, p->guidance, ctx->cfg.out_channels, p->Hl, p->Wl, nullptr, p->latents, p->q.sigma_cur,
                         p->q.sigma_next, 1, nullptr, s));

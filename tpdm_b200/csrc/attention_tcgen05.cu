@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   }
   pdl_wait();
   if (A.skip != nullptr && *A.skip != 0) return;
+  if (A.bmask != nullptr && A.bmask[blockIdx.z % A.bslots] == 0) return;  // emptied queue slot
   if (warp == 2) {
     tmem_alloc<L::kTmemCols>(tmem_slot);
     tmem_relinquish();
@@ -448,6 +449,8 @@ int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int 
 int attn_launch(const AttnOp* op_in, cudaStream_t stream) {
   AttnOp op_copy = *op_in;
   op_copy.skip = skip_flag();
+  op_copy.bmask = batch_mask();
+  op_copy.bslots = batch_mask_slots();
   const AttnOp* op = &op_copy;
   return op->dp == 64 ? attn_launch_impl<64>(*op, stream) : attn_launch_impl<128>(*op, stream);
 }

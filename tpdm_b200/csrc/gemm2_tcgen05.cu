@@ -41,6 +41,8 @@ struct Gemm2Params {
   int n_ops;
   int tiles0, total_tiles;  // pair tiles of op 0 / of all ops
   const int* skip;
+  const int* bmask;
+  int bslots;
 };
 
 struct PairCoord {
@@ -161,6 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters) {
         const PairCoord tc = decode_pair(P, tile);
+        if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
         const GemmOp& G = P.op[tc.g];
         const int nkb = (G.K + BK - 1) / BK;
         const int m0 = tc.mtp * 2 * BM + static_cast<int>(rank) * BM;
@@ -190,6 +193,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters) {
         const PairCoord tc = decode_pair(P, tile);
+        if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
         const GemmOp& G = P.op[tc.g];
         const int nkb = (G.K + BK - 1) / BK;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -234,6 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < P.total_tiles; tile += num_clusters) {
       const PairCoord tc = decode_pair(P, tile);
+        if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
       const GemmOp& G = P.op[tc.g];
       const int n0 = tc.nt * BN2;
       const int row_base = tc.mtp * 2 * BM + static_cast<int>(rank) * BM + q * 32;
@@ -265,6 +270,8 @@ int gemm2_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {
   P.total_tiles = 0;
   P.tiles0 = 0;
   P.skip = skip_flag();
+  P.bmask = batch_mask();
+  P.bslots = batch_mask_slots();
   double flops = 0;
   for (int i = 0; i < n_ops; ++i) {
     TPDM_CHECK(ops[i].conv == 0 && ops[i].block_n == 256, TPDM_ERR_ARG, "gemm2_launch: plain GEMMs with 256-wide N tiles only");

@@ -35,6 +35,8 @@ struct GemmParams {
   int n_ops;
   int total_tiles;
   const int* skip;
+  const int* bmask;  // set_batch_mask: tiles of inactive batch entries are skipped by every role
+  int bslots;
 };
 
 template <int BN>
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(P, tile);
+        if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
         const GemmOp& G = P.op[tc.g];
         const int nkb = (G.K + BK - 1) / BK;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(P, tile);
+        if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
       const GemmOp& G = P.op[tc.g];
       const int nkb = (G.K + BK - 1) / BK;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -205,6 +209,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(P, tile);
+        if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
       const GemmOp& G = P.op[tc.g];
       const int n0 = tc.nt * BN;
       const int row_base = tc.mt * BM + q * 32;
@@ -372,6 +377,8 @@ int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {
   P.n_ops = n_ops;
   P.total_tiles = 0;
   P.skip = skip_flag();
+  P.bmask = batch_mask();
+  P.bslots = batch_mask_slots();
   for (int i = 0; i < n_ops; ++i) {
     P.op[i] = ops[i];
     P.total_tiles += ops[i].num_tiles;

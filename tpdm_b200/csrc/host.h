@@ -47,6 +47,11 @@ void prof_end(cudaStream_t s);
 // denoising step enqueued speculatively after the trajectory has finished costs only empty launches.
 void set_skip_flag(const int* device_flag);
 const int* skip_flag();
+// Per-slot activity mask of the device-side prompt queue: slot_active[b % slots] == 0 makes the heavy kernels skip the tiles /
+// CTAs / rows of batch entry b (an emptied slot at the tail of the queue then costs nothing).  nullptr = everything runs.
+void set_batch_mask(const int* slot_active, int slots);
+const int* batch_mask();
+int batch_mask_slots();
 
 // Launch with programmatic stream serialization (see pdl_wait in common.cuh); TPDM_PDL=0 turns the attribute off.
 bool pdl_enabled();
@@ -127,6 +132,8 @@ struct alignas(64) AttnOp {
   int q_tiles, head_dim;
   float scale_log2;           // log2(e) / sqrt(head_dim)
   const int* skip;            // see set_skip_flag
+  const int* bmask = nullptr; // see set_batch_mask
+  int bslots = 1;
   __nv_bfloat16* out;         // [Bt][S][H*dp]
 };
 int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int head_dim, void* out);

@@ -260,6 +260,8 @@ struct LnParams {
   int nseg, D;
   long long blocks0, blocks_total;  // blocks of segment 0 / of both segments
   const int* skip;
+  const int* bmask;
+  int bslots;
 };
 
 // One block = 32 consecutive token rows of ONE batch entry of one stream: the batch entry's shift / scale vectors are
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant_
   const int blk = blockIdx.x - (si ? static_cast<int>(P.blocks0) : 0);
   const int rb_per_batch = (S.rows + kLnRowsPerBlock - 1) / kLnRowsPerBlock;
   const int b = blk / rb_per_batch, r0 = (blk - b * rb_per_batch) * kLnRowsPerBlock;
+  if (P.bmask != nullptr && P.bmask[b % P.bslots] == 0) return;  // emptied queue slot (uniform over the block)
   const float* sh = S.shift + static_cast<long long>(b) * S.mod_stride;
   const float* sc = S.scale + static_cast<long long>(b) * S.mod_stride;
   for (int k = threadIdx.x * 4; k < P.D; k += 256 * 4) {
@@ -777,6 +780,7 @@ __global__ void queue_advance_kernel(const QueueArgs a) {
     a.slot_flush[i] = flush;
     a.slot_load[i] = load;
     holds = prompt >= 0 ? 1 : 0;
+    a.slot_active[i] = holds;
   }
   const int n = __syncthreads_count(holds);
   if (i == 0) {
@@ -869,6 +873,8 @@ int k_ln_modulate(const LnSeg* segs, int nseg, int D, cudaStream_t s) {
   P.nseg = nseg;
   P.D = D;
   P.skip = skip_flag();
+  P.bmask = batch_mask();
+  P.bslots = batch_mask_slots();
   P.seg[0] = segs[0];
   P.seg[1] = nseg > 1 ? segs[1] : segs[0];
   auto blocks_of = [](const LnSeg& g) { return static_cast<long long>(g.batch) * ((g.rows + kLnRowsPerBlock - 1) / kLnRowsPerBlock); };

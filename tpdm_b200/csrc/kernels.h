@@ -86,6 +86,7 @@ struct QueueArgs {
   int* slot_step;            // [B] steps done on that prompt
   int* slot_flush;           // [B] out: prompt id whose final latent must be written out (-1: none)
   int* slot_load;            // [B] out: 1 = a new prompt was assigned to the slot (its inputs must be loaded)
+  int* slot_active;          // [B] out: 1 = the slot holds a prompt (set_batch_mask of the next step)
   int* ticket;               // next prompt id; may live in peer / pinned memory shared by several GPUs
   int* out_steps;            // [P]
   float* out_sigmas;         // [P][max_steps + 1] or null

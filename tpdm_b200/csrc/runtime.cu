@@ -27,6 +27,14 @@ int fail(int code, const char* fmt, ...) {
 static thread_local const int* g_skip = nullptr;
 void set_skip_flag(const int* f) { g_skip = f; }
 const int* skip_flag() { return g_skip; }
+static thread_local const int* g_bmask = nullptr;
+static thread_local int g_bslots = 1;
+void set_batch_mask(const int* m, int slots) {
+  g_bmask = m;
+  g_bslots = slots > 0 ? slots : 1;
+}
+const int* batch_mask() { return g_bmask; }
+int batch_mask_slots() { return g_bslots; }
 
 static std::atomic<long long> g_launches{0};
 bool pdl_enabled() {

@@ -186,8 +186,18 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
     const int ty = n / gw, tx = n - ty * gw;
     in_s[i] = lat[((static_cast<long long>(bl) * C + c) * Hl + 2 * ty + p) * Wl + 2 * tx + q];
   }
-  __syncthreads();
+  // per-token element offsets, computed once per block (the divisions, the scramble and the 64-bit address arithmetic
+  // used to be redone by every thread for every token: 200 instructions per token and warp, half of them for this)
+  __shared__ int pos_off[kPatchTok], x_off[kPatchTok], tpm_off[kPatchTok];
   const int top = (pos_max - gh) / 2, left = (pos_max - gw) / 2;
+  if (threadIdx.x < kPatchTok) {
+    const int n = n0 + threadIdx.x;
+    const int ty = n / gw, tx = n - ty * gw;
+    pos_off[threadIdx.x] = ((top + ty) * pos_max + left + tx) * D;
+    x_off[threadIdx.x] = n * D;
+    tpm_off[threadIdx.x] = scramble_pixel(n, gw) * (2 * D);
+  }
+  __syncthreads();
   for (int d = blockIdx.z * blockDim.x + threadIdx.x; d < D; d += gridDim.z * blockDim.x) {
     float w[64];
     const float* wr = Wp + static_cast<long long>(d) * KK;
@@ -200,13 +210,13 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
     // Four tokens at a time: their four pos-table loads are issued together before the FMA block (one exposed global-load
     // latency per token made the first version latency-bound at 107 us for SD3-medium), and the four accumulator chains
     // are independent.  k_patchify guarantees C*4 == 64 and N % kPatchTok == 0.
+    const long long xb = static_cast<long long>(bl) * N * D + d, xdup = static_cast<long long>(Bl) * N * D;
+    bf16* tpm_b = tpm_x ? tpm_x + static_cast<long long>(bl) * N * (2 * D) + d : nullptr;
     for (int t0 = 0; t0 < kPatchTok; t0 += 4) {
       float pv[4], acc[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int n = n0 + t0 + u;
-        const int ty = n / gw, tx = n - ty * gw;
-        pv[u] = pos[(static_cast<long long>(top + ty) * pos_max + left + tx) * D + d];
+        pv[u] = pos[pos_off[t0 + u] + d];
         acc[u] = bs;
       }
 #pragma unroll
@@ -222,14 +232,13 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int n = n0 + t0 + u;
         const float r_ = acc[u] + pv[u];
+        const long long o = xb + x_off[t0 + u];
         for (int r = 0; r < dup; ++r) {
-          const long long o = (static_cast<long long>(bl + r * Bl) * N + n) * D + d;
-          x[o] = r_;
-          if (h1_out) h1_out[o] = r_;
+          x[o + r * xdup] = r_;
+          if (h1_out) h1_out[o + r * xdup] = r_;
         }
-        if (tpm_x) tpm_x[(static_cast<long long>(bl) * N + scramble_pixel(n, gw)) * (2 * D) + d] = __float2bfloat16(r_);
+        if (tpm_b) tpm_b[tpm_off[t0 + u]] = __float2bfloat16(r_);
       }
     }
   }
@@ -593,7 +602,26 @@ __global__ void __launch_bounds__(1024) tpm_tail_kernel(const float* __restrict_
   const int b = blockIdx.x, t = threadIdx.x & 127, grp = threadIdx.x >> 7;
   const float* p = y2 + static_cast<long long>(b) * go * go * C;
   float mx = -INFINITY;
-  if (t < C) {
+  if (t < C && go == 32) {
+    // exact 2x2 windows: 8 cells (32 independent loads) in flight per batch.  The generic loop below has run-time window
+    // bounds, is not unrolled and walked its 128 loads one DRAM/L2 round trip at a time (80 us for one block).
+#pragma unroll
+    for (int c8 = 0; c8 < 4; ++c8) {
+      float v[8][4];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int cell = grp * 32 + c8 * 8 + u;
+        const int i = cell >> 4, j = cell & 15;
+        const float* q = p + (static_cast<long long>(2 * i) * 32 + 2 * j) * C + t;
+        v[u][0] = q[0];
+        v[u][1] = q[C];
+        v[u][2] = q[32 * C];
+        v[u][3] = q[33 * C];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) mx = fmaxf(mx, (((v[u][0] + v[u][1]) + v[u][2]) + v[u][3]) / 4.f);
+    }
+  } else if (t < C) {
 #pragma unroll 4
     for (int cell = grp * 32; cell < grp * 32 + 32; ++cell) {  // unrolled: the cells' loads are independent and stay in flight together
       const int i = cell >> 4, j = cell & 15;

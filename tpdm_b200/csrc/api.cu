@@ -60,7 +60,8 @@ struct tpdm_plan {
   bf16 *xn2_img = nullptr, *qkv2 = nullptr, *attn_o2 = nullptr;  // dual-attention blocks only
   // TimePredictor
   bf16* tpm_x;
-  float *y1, *a2, *y2, *tpm_emb, *temb_cfg, *alpha_beta;
+  float *y1, *y1p, *a2, *y2, *tpm_emb, *temb_cfg, *alpha_beta;
+  int conv1_split = 1;  // split-K factor of TimePredictor.conv1 (few M tiles, K = 9 * 2D)
   double* gn_stats;
   // sampling state
   float *latents, *velocity, *sigma_hist, *alphas, *betas, *logprobs, *tembs, *history, *ratios;
@@ -116,6 +117,7 @@ void carve(tpdm_plan* p, Carver& c) {
   p->enc_bf16 = c.take<bf16>(Bt * T * ctx->cfg.joint_attention_dim);
   p->tpm_x = c.take<bf16>(Bt * g * g * 2 * D);  // Bt (not B) rows so the stand-alone TPM entry point can take Bt samples
   p->y1 = c.take<float>(Bt * g * g * C1);
+  p->y1p = c.take<float>(4 * Bt * g * g * C1);  // partial products of the split-K conv1
   p->a2 = c.take<float>(Bt * g * g * C1);
   p->y2 = c.take<float>(Bt * (g / 2) * (g / 2) * C1);
   p->tpm_emb = c.take<float>(Bt * 2 * C1);
@@ -153,8 +155,20 @@ int build_ops(tpdm_plan* p) {
   const int Bt = p->Bt, N = p->N, T = p->T, S = p->S;
   const tpdm_weights& w = ctx->w;
   if (ctx->has_tpm)
-    TPDM_TRY(gemm_op_init_conv3x3(&p->conv1, p->tpm_x, Bt, p->g, 2 * D, w.tpm_conv1_w, ctx->cfg.tpm_channels, EPI_BIAS_F32, p->y1,
-                                  ctx->cfg.tpm_channels, w.tpm_conv1_b));
+    {
+      // conv1 has g*g/128 M tiles per sample and K = 9 * 2D: with one prompt in flight that is 32 CTAs walking 432 k-blocks each.
+      // K is cut in 4 (deterministic partial products, summed with the bias by k_sum_partials) when it divides evenly.
+      const int nkb = 9 * 2 * D / 64;
+      p->conv1_split = nkb % 4 == 0 ? 4 : 1;
+      if (p->conv1_split > 1) {
+        TPDM_TRY(gemm_op_init_conv3x3(&p->conv1, p->tpm_x, Bt, p->g, 2 * D, w.tpm_conv1_w, ctx->cfg.tpm_channels, EPI_BIAS_F32, p->y1p,
+                                      ctx->cfg.tpm_channels, nullptr));
+        TPDM_TRY(gemm_op_set_ksplit(&p->conv1, p->conv1_split));
+      } else {
+        TPDM_TRY(gemm_op_init_conv3x3(&p->conv1, p->tpm_x, Bt, p->g, 2 * D, w.tpm_conv1_w, ctx->cfg.tpm_channels, EPI_BIAS_F32, p->y1,
+                                      ctx->cfg.tpm_channels, w.tpm_conv1_b));
+      }
+    }
   if (!ctx->has_mmdit) return 0;
   p->blk.resize(L);
   for (int i = 0; i < L; ++i) {
@@ -291,8 +305,10 @@ int run_tpm(tpdm_plan* p, int nb, const float* temb, float* alpha_beta, cudaStre
   const int C1 = ctx->cfg.tpm_channels, g = p->g, D = ctx->D;
   GemmOp conv = p->conv1;
   conv.batch = nb;
-  conv.num_tiles = nb * conv.tiles_m_per_batch * conv.tiles_n;
+  conv.num_tiles = nb * conv.tiles_m_per_batch * conv.tiles_n * conv.ksplit;
   TPDM_TRY(gemm_launch(&conv, 1, s));
+  if (conv.ksplit > 1)
+    TPDM_TRY(k_sum_partials(p->y1p, conv.ksplit, static_cast<long long>(nb) * g * g * C1, w.tpm_conv1_b, C1, p->y1, s));
   TPDM_CUDA_OK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 2 * nb, s));
   TPDM_TRY(k_gn_stats(p->y1, p->gn_stats, nb, static_cast<long long>(g) * g * C1, s));
   TPDM_TRY(k_gemv_f32(w.tpm_lin_w, w.tpm_lin_b, temb, D, nullptr, p->tpm_emb, 2 * C1, nb, 2 * C1, D, 1, s));

@@ -50,7 +50,7 @@ struct GemmSmem {
 };
 
 struct TileCoord {
-  int g, b, mt, nt;
+  int g, b, mt, nt, ks;
 };
 
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) {
@@ -61,6 +61,9 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& P, int tile) 
   // N fastest: the n-tiles that share an A row-block run in the same wave, so A is fetched from DRAM once (the others hit
   // L2) and the weight matrix -- the operand every CTA re-reads -- stays L2 resident.  (M fastest re-read A once per wave:
   // ncu showed 408 MB of DRAM reads for FF2 against 170 MB algorithmic.)
+  const int per_split = G.num_tiles / G.ksplit;
+  t.ks = local / per_split;  // K range of a split-K op (0 otherwise)
+  local -= t.ks * per_split;
   int m_idx = local / G.tiles_n;
   t.nt = local - m_idx * G.tiles_n;
   t.b = m_idx / G.tiles_m_per_batch;
@@ -121,8 +124,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
         const TileCoord tc = decode_tile(P, tile);
         if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
         const GemmOp& G = P.op[tc.g];
-        const int nkb = (G.K + BK - 1) / BK;
-        for (int kb = 0; kb < nkb; ++kb) {
+        const int nkb_all = (G.K + BK - 1) / BK, kps = (nkb_all + G.ksplit - 1) / G.ksplit;
+        const int kb0 = tc.ks * kps, nkb = kb0 + kps < nkb_all ? kb0 + kps : nkb_all;
+        for (int kb = kb0; kb < nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * L::kStageBytes;
           uint8_t* sB = sA + kABytes;
@@ -170,11 +174,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       const TileCoord tc = decode_tile(P, tile);
         if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
       const GemmOp& G = P.op[tc.g];
-      const int nkb = (G.K + BK - 1) / BK;
+      const int nkb_all = (G.K + BK - 1) / BK, kps = (nkb_all + G.ksplit - 1) / G.ksplit;
+      const int kb0 = tc.ks * kps, nkb = kb0 + kps < nkb_all ? kb0 + kps : nkb_all;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kb = kb0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
             const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);
           if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
@@ -214,7 +219,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       const int n0 = tc.nt * BN;
       const int row_base = tc.mt * BM + q * 32;
       gemm_epilogue_tile<BN>(
-          G, tc.b, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, st, sbias, lane, 0, BN / 32,
+          G, tc.b + tc.ks * G.batch, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, st, sbias, lane, 0, BN / 32,
           [&]() { mbar_wait(&tmem_full[acc], acc_phase); }, [&]() { if (lane == 0) mbar_arrive(&tmem_empty[acc]); });
       if (++acc == 2) {
         acc = 0;
@@ -369,6 +374,17 @@ int gemm_op_init_conv3x3_wgrad(GemmOp* op, const void* dYt, const void* Xnchw, i
   uint64_t bstr[3] = {static_cast<uint64_t>(P) * 2, static_cast<uint64_t>(P) * C * 2, static_cast<uint64_t>(P) * C * 3 * 2};
   uint32_t bbox[4] = {BK, 256, 1, 1};
   return encode_tmap_bf16(&op->tmB, Xnchw, 4, bdims, bstr, bbox);
+}
+
+int gemm_op_set_ksplit(GemmOp* op, int ksplit) {
+  const int nkb = (op->K + BK - 1) / BK;
+  TPDM_CHECK(ksplit >= 1 && ksplit <= nkb, TPDM_ERR_ARG, "gemm: ksplit %d outside [1, %d]", ksplit, nkb);
+  TPDM_CHECK(ksplit == 1 || (op->epi == EPI_BIAS_F32 && op->bias == nullptr && op->conv != 2 && op->block_n == 128), TPDM_ERR_ARG,
+             "gemm: split K needs a bias-free fp32 output on the 128-wide 1-CTA kernel");
+  TPDM_CHECK((nkb + ksplit - 1) / ksplit * (ksplit - 1) < nkb, TPDM_ERR_ARG, "gemm: ksplit %d leaves an empty K range", ksplit);
+  op->num_tiles = op->num_tiles / op->ksplit * ksplit;
+  op->ksplit = ksplit;
+  return 0;
 }
 
 int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {

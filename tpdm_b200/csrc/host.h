@@ -93,6 +93,8 @@ struct alignas(64) GemmOp {
   int tiles_m_per_batch, tiles_n, num_tiles, block_n;
   int conv, conv_by, kb_per_tap, epi;  // conv: 0 plain, 1 conv3x3 forward, 2 conv3x3 weight gradient
   int conv_bx = 0, conv_xt = 1;        // conv 1: pixels per tile row segment, tile segments per image row
+  int ksplit = 1;                      // 1-CTA kernel: K is cut into `ksplit` ranges, range s writes out + (s*batch + b)*out_batch_stride
+                                       // (partial sums, to be added by the consumer); see gemm_op_set_ksplit
   const void* res = nullptr;           // EPI_BIAS_ADD_BF16: bf16 addend, indexed exactly like `out` (may alias it)
   int wg_px, wg_bpr, wg_ctiles, wg_pad;
   void* out;
@@ -118,6 +120,8 @@ int gemm_op_init_conv3x3_hw(GemmOp* op, const void* X, int batch, int H, int Wd,
 // dYt bf16 [samples][M][g*g]; X bf16 as THREE x-shifted NCHW copies [samples][3][C][g][g], copy k holding X[.., x + k - 1]
 // (zero outside), so no TMA load needs an unaligned innermost coordinate; dW fp32 [M][9][C] (overwritten)
 int gemm_op_init_conv3x3_wgrad(GemmOp* op, const void* dYt, const void* Xnchw, int samples, int g, int C, int M, float* dW);
+// split K of a bias-free fp32-output op of the 1-CTA kernel into `ksplit` partial products (more CTAs for few-tile problems)
+int gemm_op_set_ksplit(GemmOp* op, int ksplit);
 // one persistent launch over up to two ops (e.g. image stream + text stream)
 int gemm_launch(const GemmOp* ops, int n_ops, cudaStream_t stream);
 // CTA-pair (cta_group::2) kernel for plain GEMMs with 256-wide N tiles; gemm_launch dispatches to it

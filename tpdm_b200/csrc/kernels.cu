@@ -749,6 +749,18 @@ __global__ void schedule_kernel(const ScheduleArgs a) {
   if (i == 0) a.all_done[a.step] = all;
 }
 
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int splits, long long n, const float* __restrict__ bias,
+                                                           int C, float* __restrict__ y) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = bias ? ld4(bias + static_cast<int>(i % C)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = ld4(part + s * n + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(y + i) = acc;
+}
+
 // ---- device-side prompt queue ---------------------------------------------------------------------------------
 // predict-mode schedule update per slot (modeling_sd3_pnt.py:557-590 with ratio = Beta mode), sigma kept per slot
 __global__ void queue_schedule_kernel(const QueueArgs a) {
@@ -1009,6 +1021,14 @@ int k_tpm_tail(const float* y2, int B, int go, int C, const float* fc1_w, const 
                float eps, float* alpha_beta, cudaStream_t s) {
   TPDM_CHECK(C <= 128 && C % 32 == 0, TPDM_ERR_SHAPE, "tpm_tail: conv_out_channels %d must be a multiple of 32, <= 128", C);
   tpm_tail_kernel<<<B, 1024, 0, s>>>(y2, go, C, fc1_w, fc1_b, fc2_w, fc2_b, eps, alpha_beta);
+  count_launch();
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int k_sum_partials(const float* part, int splits, long long n, const float* bias, int C, float* y, cudaStream_t s) {
+  TPDM_CHECK(n % 4 == 0 && C % 4 == 0 && splits >= 1, TPDM_ERR_SHAPE, "sum_partials: n and C must be multiples of 4");
+  sum_partials_kernel<<<blocks_for(n / 4, 256), 256, 0, s>>>(part, splits, n, bias, C, y);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

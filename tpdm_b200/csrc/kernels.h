@@ -75,6 +75,8 @@ struct ScheduleArgs {
   int B, T, step, predict, relative, prediction_type;
   float min_sigma, epsilon;
 };
+// y[i] = bias[i % C] + sum_s part[s * n + i]: adds up the partial products of a split-K GEMM (n % 4 == 0, C % 4 == 0)
+int k_sum_partials(const float* part, int splits, long long n, const float* bias, int C, float* y, cudaStream_t s);
 int k_schedule(const ScheduleArgs& a, cudaStream_t s);
 
 // ---- device-side prompt queue (continuous batching over a fixed number of in-flight slots) ---------------------------

@@ -2,6 +2,7 @@
 // Each kernel names the reference code it replaces (paths relative to /root/reference).
 #include <curand_kernel.h>
 #include <math.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "host.h"
@@ -856,6 +857,100 @@ __global__ void __launch_bounds__(256) queue_move_kernel(const int* __restrict__
   }
 }
 
+// LayerNorm + modulation with the rows STAGED THROUGH SHARED MEMORY by 1-D bulk async copies (cp.async.bulk, the TMA engine):
+// every warp owns kLnSlots row slots and keeps that many rows in flight without spending registers on them -- while a row
+// is reduced, normalised and stored, the copies of the warp's next rows are already running.  The register-only kernel
+// above reaches 3.4 TB/s of DRAM reads (each warp waits out a full memory round trip per row); same block -> rows mapping.
+constexpr int kLnSlots = 2;
+
+__device__ __forceinline__ void bulk_load_row(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256, 2) ln_modulate_bulk_kernel(const __grid_constant__ LnParams P) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) float ln_smem[];  // [D] shift, [D] 1 + scale, then 8 warps x kLnSlots rows of D floats
+  __shared__ uint64_t bars[8 * kLnSlots];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int D = VPL * 128;
+  float* ring = ln_smem + 2 * D + warp * kLnSlots * D;
+  if (lane == 0) {
+    for (int i = 0; i < kLnSlots; ++i) mbar_init(&bars[warp * kLnSlots + i], 1);
+    fence_barrier_init();
+  }
+  __syncwarp();
+  pdl_wait();
+  if (P.skip != nullptr && *P.skip != 0) return;
+  const int si = static_cast<long long>(blockIdx.x) >= P.blocks0 ? 1 : 0;
+  const LnSeg& S = P.seg[si];
+  const int blk = blockIdx.x - (si ? static_cast<int>(P.blocks0) : 0);
+  const int rb_per_batch = (S.rows + kLnRowsPerBlock - 1) / kLnRowsPerBlock;
+  const int b = blk / rb_per_batch, r0 = (blk - b * rb_per_batch) * kLnRowsPerBlock;
+  if (P.bmask != nullptr && P.bmask[b % P.bslots] == 0) return;  // emptied queue slot (uniform over the block)
+  // this warp's rows: r0 + warp, r0 + warp + 8, ...  (kLnRowsPerBlock / 8 of them); start the first kLnSlots copies
+  const long long row0 = static_cast<long long>(b) * S.rows;
+  auto row_ok = [&](int j) { return j < kLnRowsPerBlock / 8 && r0 + warp + 8 * j < S.rows; };
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < kLnSlots; ++j)
+      if (row_ok(j)) {
+        mbar_arrive_expect_tx(&bars[warp * kLnSlots + j], D * 4);
+        bulk_load_row(ring + j * D, S.x + (row0 + r0 + warp + 8 * j) * D, D * 4, &bars[warp * kLnSlots + j]);
+      }
+  }
+  const float* sh = S.shift + static_cast<long long>(b) * S.mod_stride;
+  const float* sc = S.scale + static_cast<long long>(b) * S.mod_stride;
+  for (int k = threadIdx.x * 4; k < D; k += 256 * 4) {
+    *reinterpret_cast<float4*>(ln_smem + k) = ld4(sh + k);
+    float4 c = ld4(sc + k);
+    c.x += 1.f; c.y += 1.f; c.z += 1.f; c.w += 1.f;
+    *reinterpret_cast<float4*>(ln_smem + D + k) = c;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int j = 0; j < kLnRowsPerBlock / 8; ++j) {
+    if (!row_ok(j)) break;
+    const int slot = j % kLnSlots;
+    uint64_t* bar = &bars[warp * kLnSlots + slot];
+    mbar_wait(bar, (j / kLnSlots) & 1);
+    const float* src = ring + slot * D;
+    float4 v[VPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i] = *reinterpret_cast<const float4*>(src + (i * 32 + lane) * 4);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    __syncwarp();
+    if (lane == 0 && row_ok(j + kLnSlots)) {  // the slot is free again: refill it for the row after next
+      fence_proxy_async();                  // generic-proxy reads above are ordered before the async-proxy write below
+      mbar_arrive_expect_tx(bar, D * 4);
+      bulk_load_row(ring + slot * D, S.x + (row0 + r0 + warp + 8 * (j + kLnSlots)) * D, D * 4, bar);
+    }
+    const float mean = warp_sum(s) / D;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float a = v[i].x - mean, bq = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + bq * bq) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / D + 1e-6f);
+    bf16* o = S.out + (row0 + r0 + warp + 8 * j) * D;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int k = (i * 32 + lane) * 4;
+      const float4 h = *reinterpret_cast<const float4*>(ln_smem + k), c = *reinterpret_cast<const float4*>(ln_smem + D + k);
+      uint2 w;
+      w.x = pack_bf16x2((v[i].x - mean) * rstd * c.x + h.x, (v[i].y - mean) * rstd * c.y + h.y);
+      w.y = pack_bf16x2((v[i].z - mean) * rstd * c.z + h.z, (v[i].w - mean) * rstd * c.w + h.w);
+      *reinterpret_cast<uint2*>(o + k) = w;
+    }
+  }
+}
+
 inline unsigned blocks_for(long long n, int per) { return static_cast<unsigned>((n + per - 1) / per); }
 
 }  // namespace
@@ -926,7 +1021,16 @@ int k_ln_modulate(const LnSeg* segs, int nseg, int D, cudaStream_t s) {
   double bytes = 0;  // profile class 2: algorithmic bytes = one fp32 read + one bf16 write per element
   for (int i = 0; i < nseg; ++i) bytes += 6.0 * segs[i].batch * segs[i].rows * D;
   prof_begin(2, bytes, s);
-  if (D == 1536)
+  static const bool bulk = getenv("TPDM_LN_BULK") == nullptr || atoi(getenv("TPDM_LN_BULK")) != 0;
+  if (D == 1536 && bulk) {
+    const size_t smem_b = (2 + 8 * kLnSlots) * static_cast<size_t>(D) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      TPDM_CUDA_OK(cudaFuncSetAttribute(ln_modulate_bulk_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_b)));
+      attr = true;
+    }
+    TPDM_CUDA_OK(launch_pdl(ln_modulate_bulk_kernel<12>, dim3(grid), dim3(256), smem_b, s, P));
+  } else if (D == 1536)
     TPDM_CUDA_OK(launch_pdl(ln_modulate_kernel<12>, dim3(grid), dim3(256), smem, s, P));
   else if (D == 384)
     TPDM_CUDA_OK(launch_pdl(ln_modulate_kernel<3>, dim3(grid), dim3(256), smem, s, P));

@@ -391,7 +391,7 @@ class Engine:
         nbytes = lib.tpdm_queue_workspace_bytes(plan.handle, P)
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
         base = (ws.data_ptr() + 1023) // 1024 * 1024
-        active_host = torch.ones(4096, dtype=torch.int32).pin_memory()
+        active_host = torch.ones(64, dtype=torch.int32).pin_memory()
         # the step is replayed from a CUDA graph (captured on the first step), which needs a non-default stream
         qs = getattr(self, "_queue_stream", None)
         if qs is None:
@@ -406,20 +406,27 @@ class Engine:
             L.check(lib.tpdm_queue_status(plan.handle, C.byref(act_p), C.byref(slot_p)))
             off = act_p.value - ws.data_ptr()          # the counters live in the queue workspace
             active = ws[off: off + 4].view(torch.int32)
-            events = []
-            limit = (P + slots - 1) // slots * max_inference_steps + 2 * max_inference_steps
+            ring = active_host.numel()
+            events = [None] * ring
+            limit = (P + slots - 1) // slots * max_inference_steps + 2 * max_inference_steps   # upper bound on device steps
             steps_run = 0
-            for it in range(min(limit, active_host.numel())):
+            drained = False
+            for it in range(limit):
                 L.check(step_fn(plan.handle, stream))
                 steps_run += 1
-                active_host[it: it + 1].copy_(active, non_blocking=True)
+                active_host[it % ring: it % ring + 1].copy_(active, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
-                events.append(ev)
+                events[it % ring] = ev
                 if it >= 1:                      # look at the flag one step late: the device never waits for the host
-                    events[it - 1].synchronize()
-                    if int(active_host[it - 1]) == 0:
+                    events[(it - 1) % ring].synchronize()
+                    if int(active_host[(it - 1) % ring]) == 0:
+                        drained = True
                         break
+            if not drained:
+                torch.cuda.current_stream().synchronize()
+                if int(active.item()) != 0:
+                    raise RuntimeError("sample_queue: the queue did not drain within the step bound")
             torch.cuda.current_stream().synchronize()
         torch.cuda.current_stream(dev).wait_stream(qs)
         self._queue_keepalive = (ws, lat, pe, ne, pp, npp, ticket)

@@ -164,3 +164,17 @@ def test_only_predict_logprobs_replays_sampling(tiny):
     assert torch.allclose(lp, out["logprobs"], atol=1e-4)
     with pytest.raises(ValueError):
         pipe.only_predict_logprobs(None, None, None)
+
+
+def test_product_get_ref_beta_equals_pinned_oracle():
+    """tpdm_b200.reference_distributions.get_ref_beta (host helper kept for callers of the reference API) is bit-identical to
+    the oracle's copy, which make_golden.py pins against the reference's own function."""
+    from oracle import sd3_oracle as O
+    from tpdm_b200.reference_distributions import get_ref_beta
+
+    s = torch.rand(4096, generator=torch.Generator().manual_seed(3)) * 0.995 + 0.004
+    a, b = get_ref_beta(s)
+    ra, rb = O.get_ref_beta(s)
+    assert torch.equal(a, ra) and torch.equal(b, rb)
+    a1, b1 = get_ref_beta(torch.tensor([1.0]), num_steps=28)
+    assert abs(float(a1) - 18.758) < 1e-3 and abs(float(b1) - 1.242) < 1e-3

@@ -534,3 +534,48 @@ def test_mmdit_sd35_large_width_vs_oracle():
         rv, rt, rh1, rh2 = ora(lat, enc, pooled, ts)
     v, temb, h1, h2 = model(lat, enc, pooled, ts, return_dict=False)
     assert rel(temb, rt) < 2e-3 and rel(h1, rh1) < 1e-3 and rel(h2, rh2) < VEL_TOL and rel(v, rv) < VEL_TOL
+
+
+def test_ln_modulate_full_size_properties(L):
+    """SD3-medium block shape (2 x 4096 rows of 1536): with zero shift / scale every output row is standardised; a constant
+    shift moves the row mean, a constant scale the row spread; rows do not influence each other (permutation equivariance)."""
+    torch.manual_seed(12)
+    lib = L.load()
+    B, rows, D = 2, 4096, 1536
+    x = torch.randn(B, rows, D, device="cuda") * torch.rand(B, rows, 1, device="cuda").mul(5).add(0.1) + torch.randn(B, rows, 1, device="cuda") * 4
+    out = torch.empty(B, rows, D, device="cuda", dtype=torch.bfloat16)
+
+    def run(inp, mod):
+        L.check(lib.tpdm_ln_modulate(L.ptr(inp), mod.data_ptr(), mod.data_ptr() + 4 * D, 2 * D, L.ptr(out), B, rows, D, None))
+        torch.cuda.synchronize()
+        return out.float().clone()
+
+    zero = torch.zeros(B, 2 * D, device="cuda")
+    y = run(x, zero)
+    assert float(y.mean(-1).abs().max()) < 2e-2 and float((y.var(-1, unbiased=False) - 1).abs().max()) < 2e-2
+    mod = zero.clone()
+    mod[:, :D] = 0.75       # shift
+    mod[:, D:] = 1.0        # scale -> factor 2
+    y2 = run(x, mod)
+    assert float((y2.mean(-1) - 0.75).abs().max()) < 3e-2 and float((y2.var(-1, unbiased=False) - 4).abs().max()) < 8e-2
+    perm = torch.randperm(rows, device="cuda")
+    yp = run(x[:, perm].contiguous(), zero)
+    assert torch.equal(yp, y[:, perm])
+
+
+def test_euler_step_round_trip_full_size():
+    """custom_step at the 1024^2 latent shape: stepping sigma -> sigma_next and back returns the sample (fp32 rounding only), and
+    the step is linear in the model output."""
+    from tpdm_b200.model_utilis import CustomFlowMatchEulerDiscreteScheduler
+
+    sch = CustomFlowMatchEulerDiscreteScheduler()
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(2, 16, 128, 128, device="cuda", generator=g)
+    v = torch.randn(2, 16, 128, 128, device="cuda", generator=g)
+    s0, s1 = torch.tensor([1.0, 0.62], device="cuda"), torch.tensor([0.71, 0.40], device="cuda")
+    fwd = sch.custom_step(v, s1, s0, x, return_dict=False)[0]
+    back = sch.custom_step(v, s0, s1, fwd, return_dict=False)[0]
+    assert float((back - x).abs().max()) < 1e-5
+    assert torch.allclose(fwd, x + (s1 - s0).view(-1, 1, 1, 1) * v, atol=1e-6)
+    twice = sch.custom_step(2 * v, s1, s0, x, return_dict=False)[0]
+    assert torch.allclose(twice - x, 2 * (fwd - x), atol=1e-5)

@@ -198,49 +198,57 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
     x_off[threadIdx.x] = n * D;
     tpm_off[threadIdx.x] = scramble_pixel(n, gw) * (2 * D);
   }
-  __syncthreads();
-  for (int d = blockIdx.z * blockDim.x + threadIdx.x; d < D; d += gridDim.z * blockDim.x) {
-    float w[64];
-    const float* wr = Wp + static_cast<long long>(d) * KK;
-#pragma unroll
+  // this block's 256 output channels: weights staged TRANSPOSED in shared memory (ws[k][d], row padded to 257 floats so that
+  // both the staging stores and the per-k reads are conflict-free).  Keeping the 64 weights of a channel in registers cost
+  // 128 registers per thread, two resident blocks per SM and a 2.6-wave tail (69 us); with 8 accumulators per thread the
+  // kernel fits three blocks per SM.
+  float* ws = in_s + kPatchTok * 64;  // [64][257]
+  const int d = blockIdx.z * blockDim.x + threadIdx.x;
+  if (d < D) {
+    const float* wr = Wp + static_cast<long long>(d) * 64;
+#pragma unroll 4
     for (int k = 0; k < 64; k += 4) {
-      float4 v = ld4(wr + k);
-      w[k] = v.x; w[k + 1] = v.y; w[k + 2] = v.z; w[k + 3] = v.w;
+      const float4 v = ld4(wr + k);
+      ws[(k + 0) * 257 + threadIdx.x] = v.x;
+      ws[(k + 1) * 257 + threadIdx.x] = v.y;
+      ws[(k + 2) * 257 + threadIdx.x] = v.z;
+      ws[(k + 3) * 257 + threadIdx.x] = v.w;
     }
-    const float bs = bias[d];
-    // Four tokens at a time: their four pos-table loads are issued together before the FMA block (one exposed global-load
-    // latency per token made the first version latency-bound at 107 us for SD3-medium), and the four accumulator chains
-    // are independent.  k_patchify guarantees C*4 == 64 and N % kPatchTok == 0.
-    const long long xb = static_cast<long long>(bl) * N * D + d, xdup = static_cast<long long>(Bl) * N * D;
-    bf16* tpm_b = tpm_x ? tpm_x + static_cast<long long>(bl) * N * (2 * D) + d : nullptr;
-    for (int t0 = 0; t0 < kPatchTok; t0 += 4) {
-      float pv[4], acc[4];
+  }
+  __syncthreads();
+  if (d >= D) return;
+  const float bs = bias[d];
+  const long long xb = static_cast<long long>(bl) * N * D + d, xdup = static_cast<long long>(Bl) * N * D;
+  bf16* tpm_b = tpm_x ? tpm_x + static_cast<long long>(bl) * N * (2 * D) + d : nullptr;
+  const float* wcol = ws + threadIdx.x;
+  for (int t0 = 0; t0 < kPatchTok; t0 += 8) {
+    float pv[8], acc[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        pv[u] = pos[pos_off[t0 + u] + d];
-        acc[u] = bs;
+    for (int u = 0; u < 8; ++u) {
+      pv[u] = pos[pos_off[t0 + u] + d];   // eight independent loads in flight under the FMA block
+      acc[u] = bs;
+    }
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+      const float w0 = wcol[(4 * k + 0) * 257], w1 = wcol[(4 * k + 1) * 257], w2 = wcol[(4 * k + 2) * 257], w3 = wcol[(4 * k + 3) * 257];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 v = *reinterpret_cast<const float4*>(in_s + (t0 + u) * 64 + 4 * k);  // broadcast LDS.128
+        acc[u] = fmaf(w0, v.x, acc[u]);
+        acc[u] = fmaf(w1, v.y, acc[u]);
+        acc[u] = fmaf(w2, v.z, acc[u]);
+        acc[u] = fmaf(w3, v.w, acc[u]);
       }
+    }
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float4 v = *reinterpret_cast<const float4*>(in_s + (t0 + u) * 64 + 4 * k);  // broadcast LDS.128
-          acc[u] = fmaf(w[4 * k], v.x, acc[u]);
-          acc[u] = fmaf(w[4 * k + 1], v.y, acc[u]);
-          acc[u] = fmaf(w[4 * k + 2], v.z, acc[u]);
-          acc[u] = fmaf(w[4 * k + 3], v.w, acc[u]);
-        }
+    for (int u = 0; u < 8; ++u) {
+      const float r_ = acc[u] + pv[u];
+      const long long o = xb + x_off[t0 + u];
+      for (int r = 0; r < dup; ++r) {
+        x[o + r * xdup] = r_;
+        if (h1_out) h1_out[o + r * xdup] = r_;
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float r_ = acc[u] + pv[u];
-        const long long o = xb + x_off[t0 + u];
-        for (int r = 0; r < dup; ++r) {
-          x[o + r * xdup] = r_;
-          if (h1_out) h1_out[o + r * xdup] = r_;
-        }
-        if (tpm_b) tpm_b[tpm_off[t0 + u]] = __float2bfloat16(r_);
-      }
+      if (tpm_b) tpm_b[tpm_off[t0 + u]] = __float2bfloat16(r_);
     }
   }
 }
@@ -995,8 +1003,13 @@ int k_patchify(const float* latents, const float* Wp, const float* bias, const f
   TPDM_CHECK(Hl / 2 <= pos_max && Wl / 2 <= pos_max, TPDM_ERR_SHAPE, "patchify: grid %dx%d exceeds pos_embed_max_size %d", Hl / 2,
              Wl / 2, pos_max);
   dim3 grid(N / kPatchTok, Bl, (D + 255) / 256);  // one output channel per thread: (N/32) x Bl x D/256 blocks
-  patchify_kernel<<<grid, 256, kPatchTok * 64 * sizeof(float), s>>>(latents, Wp, bias, pos_table, pos_max, x, Bl, dup, C, Hl, Wl, D,
-                                                                   h1_out, tpm_x);
+  const size_t smem = (kPatchTok * 64 + 64 * 257) * sizeof(float);  // input patches + transposed weight slice
+  static bool attr_set = false;
+  if (!attr_set) {
+    TPDM_CUDA_OK(cudaFuncSetAttribute(patchify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  patchify_kernel<<<grid, 256, smem, s>>>(latents, Wp, bias, pos_table, pos_max, x, Bl, dup, C, Hl, Wl, D, h1_out, tpm_x);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

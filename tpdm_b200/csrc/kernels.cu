@@ -218,14 +218,21 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   __syncthreads();
   if (d >= D) return;
   const float bs = bias[d];
+  // output pointers resolved once per thread; inside the token loop a store is one 32-bit offset away (the generic form --
+  // 64-bit index arithmetic and a run-time `dup` loop per token -- made address code 3x the FMA count)
   const long long xb = static_cast<long long>(bl) * N * D + d, xdup = static_cast<long long>(Bl) * N * D;
-  bf16* tpm_b = tpm_x ? tpm_x + static_cast<long long>(bl) * N * (2 * D) + d : nullptr;
+  float* const x0 = x + xb;
+  float* const x1 = dup > 1 ? x0 + xdup : nullptr;
+  float* const h0 = h1_out ? h1_out + xb : nullptr;
+  float* const h1 = (h1_out && dup > 1) ? h1_out + xb + xdup : nullptr;
+  bf16* const tpm_b = tpm_x ? tpm_x + static_cast<long long>(bl) * N * (2 * D) + d : nullptr;
+  const float* const posd = pos + d;
   const float* wcol = ws + threadIdx.x;
   for (int t0 = 0; t0 < kPatchTok; t0 += 8) {
     float pv[8], acc[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      pv[u] = pos[pos_off[t0 + u] + d];   // eight independent loads in flight under the FMA block
+      pv[u] = posd[pos_off[t0 + u]];   // eight independent loads in flight under the FMA block
       acc[u] = bs;
     }
 #pragma unroll 4
@@ -243,11 +250,11 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const float r_ = acc[u] + pv[u];
-      const long long o = xb + x_off[t0 + u];
-      for (int r = 0; r < dup; ++r) {
-        x[o + r * xdup] = r_;
-        if (h1_out) h1_out[o + r * xdup] = r_;
-      }
+      const int o = x_off[t0 + u];
+      x0[o] = r_;
+      if (x1) x1[o] = r_;
+      if (h0) h0[o] = r_;
+      if (h1) h1[o] = r_;
       if (tpm_b) tpm_b[tpm_off[t0 + u]] = __float2bfloat16(r_);
     }
   }

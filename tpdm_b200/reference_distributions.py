@@ -5,7 +5,7 @@ One step of the 28-step *shifted* flow-matching schedule is used as the prior fo
 map  sigma(t) = e t / (1 + (e - 1) t)  and its inverse  t(sigma) = sigma / (e + (1 - e) sigma),  a step of size 1/num_steps
 in t from the current sigma lands at sigma'; the prior is the Beta distribution with concentration 20 whose mode is the ratio
 sigma' / sigma.  The device version (KL against this prior) lives in csrc/tpm_train.cu::rollout_shaping_kernel; this host
-function exists for callers of the reference API and is checked against the oracle's pinned copy in the tests."""
+function exists for callers of the reference API and is checked bit for bit against the pinned restatement in the tests."""
 import math
 
 import torch

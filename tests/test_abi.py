@@ -166,3 +166,29 @@ def test_vae_oracle_shapes_and_flops():
     u8 = V.postprocess_uint8(img)
     assert u8.shape == (1, 16, 16, 3) and u8.dtype == torch.uint8
     assert abs(V.decode_flops(V.sd3_vae_config(), 128, 128) / 1e12 - 10.47) < 0.05
+
+
+def test_vae_create_validates_topology_without_a_gpu(lib):
+    """tpdm_vae_create is host-only: bad topologies are refused with TPDM_ERR_SHAPE / TPDM_ERR_ARG and a message; a valid SD3
+    configuration reports 2 + 4 * 3 resnets."""
+    from tpdm_b200 import _lib as L
+
+    def cfg(channels, groups=32, layers=2, latent=16):
+        c = L.TpdmVaeConfig(latent_channels=latent, out_channels=3, num_levels=len(channels), layers_per_block=layers,
+                            norm_num_groups=groups, scaling_factor=1.5305, shift_factor=0.0609)
+        for i, v in enumerate(channels):
+            c.block_out_channels[i] = v
+        return c
+
+    h = L.vp()
+    assert lib.tpdm_vae_create(C.byref(cfg((128, 256, 512, 512))), C.byref(h)) == 0
+    assert lib.tpdm_vae_num_resnets(h) == 14
+    assert lib.tpdm_vae_workspace_bytes(h, 128, 128) > 3 * 2**30        # 4 activation buffers of 512 MiB + attention scratch
+    assert lib.tpdm_vae_workspace_bytes(h, 0, 128) == 0
+    assert lib.tpdm_vae_destroy(h) == 0
+    bad = L.vp()
+    assert lib.tpdm_vae_create(C.byref(cfg((96, 192))), C.byref(bad)) == L.TPDM_ERR_SHAPE      # not multiples of 64
+    assert b"block_out_channels" in lib.tpdm_last_error()
+    assert lib.tpdm_vae_create(C.byref(cfg((64, 128), groups=32)), C.byref(bad)) == L.TPDM_ERR_SHAPE   # 2 channels per group
+    assert lib.tpdm_vae_create(C.byref(cfg((128,), latent=80)), C.byref(bad)) == L.TPDM_ERR_SHAPE
+    assert lib.tpdm_vae_create(None, C.byref(bad)) == L.TPDM_ERR_ARG

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TPDM_ABI_VERSION 2
+#define TPDM_ABI_VERSION 3
 
 typedef enum tpdm_status {
   TPDM_OK = 0,
@@ -208,12 +208,21 @@ int tpdm_tpm_train_forward(tpdm_tpm_trainer* t, const void* x_nhwc, const float*
                            void* stream);
 /* dz [ns][2] = d loss / d (fc2 output, i.e. log(alpha - eps), log(beta - eps)); OVERWRITES the bound grads buffer */
 int tpdm_tpm_train_backward(tpdm_tpm_trainer* t, const float* dz, void* stream);
-/* alpha_beta [mb*T][2] in (sample, step) order, sigmas / old_logprobs [mb][T] (old_logprobs with 1.0 at masked steps, as
- * the rollout returns them), advantages [mb] -> new_logprobs [mb][T], dz [mb*T][2],
- * stats4 = {loss, clip fraction, approx KL, mean ratio} (device) */
+/* alpha_beta [mb*T][2] = the TimePredictor outputs in (sample, step) order, sigmas / old_logprobs [mb][T] (old_logprobs with
+ * 1.0 at masked steps, as the rollout returns them), advantages [mb] -> new_logprobs [mb][T], dz [mb*T][2] = d loss / d (fc2
+ * output), stats4 = {loss, clip fraction, approx KL, mean ratio} (device).  prediction_type as in tpdm_config: with 1 the
+ * Beta parameters are alpha = p1 (p2 - 2) + 1, beta = (1 - p1)(p2 - 2) + 1 (modeling_sd3_pnt.py:559-563) and dz carries that
+ * chain rule, so the replay scores the same distribution the rollout drew from.  reduce_tail (NULL or 2 floats that sit right
+ * behind the flat gradient buffer): {loss or 0 when it is not finite, 1 when it is not finite else 0}; summed by the gradient
+ * all-reduce it tells every rank whether ANY rank saw a NaN / Inf loss (rloo_trainer.py:497-500). */
 int tpdm_ppo_clip_loss(const float* alpha_beta, const float* sigmas, const float* old_logprobs, const float* advantages,
-                       int mb, int T, float min_sigma, float epsilon, int relative, float cliprange, float tpm_epsilon,
-                       float* new_logprobs, float* dz, float* stats4, void* stream);
+                       int mb, int T, float min_sigma, float epsilon, int relative, int prediction_type, float cliprange,
+                       float tpm_epsilon, float* new_logprobs, float* dz, float* stats4, float* reduce_tail, void* stream);
+/* only_predict_logprobs after the TimePredictor (modeling_sd3_pnt.py:699-724): logprobs [mb][T] = Beta log-prob of the
+ * recorded ratio (sigma_next / sigma, or sigma - sigma_next when not relative; clamped to [epsilon, 1 - epsilon]), 1.0 where
+ * the sample had already finished; dlp_dz [mb*T][2] (may be NULL) = d logprob / d (fc2 output), 0 at finished steps. */
+int tpdm_beta_logprob(const float* alpha_beta, const float* sigmas, int mb, int T, float min_sigma, float epsilon,
+                      int relative, int prediction_type, float tpm_epsilon, float* logprobs, float* dlp_dz, void* stream);
 /* Reward shaping of one RLOO rollout on the device (replaces the Python loops of modeling_sd3_pnt.py:828-841 and :875-901 and
  * the tensor code of rloo_trainer.py:447-461).  alphas / betas / sigmas [batch][steps] fp32 and masks [batch][steps] int32 as
  * the sampler leaves them; last_rewards [batch] (NULL: scores = 0).  Outputs (each may be NULL): kl [batch][steps] =
@@ -225,11 +234,13 @@ int tpdm_rollout_shaping(const float* alphas, const float* betas, const float* s
                          const float* last_rewards, int batch, int steps, int relative, int ref_steps, float gamma,
                          float kl_coef, int mean_kl, int rloo_k, float* kl, float* scores, float* rlhf_reward,
                          float* advantages, void* stream);
-/* g = grads * grad_scale; clip to max_grad_norm (<= 0: off); AdamW (decoupled weight decay); non-finite norm skips the
- * update; the first bf16_n parameters are mirrored to bf16_copy.  scratch_sumsq: 1 double on the device (holds |g|^2 after). */
+/* g = grads * grad_scale; clip to max_grad_norm (<= 0: off); AdamW (decoupled weight decay); a non-finite norm, or
+ * *skip_flag != 0 (device float, NULL = none: the all-reduced non-finite-loss count of tpdm_ppo_clip_loss), skips the update
+ * (rloo_trainer.py:497-500, 518-520); the first bf16_n parameters are mirrored to bf16_copy.  scratch_sumsq: 1 double on the
+ * device (holds |g|^2 after). */
 int tpdm_adamw_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2,
                     float eps, float weight_decay, float max_grad_norm, int step, float grad_scale, double* scratch_sumsq,
-                    void* bf16_copy, long long bf16_n, void* stream);
+                    void* bf16_copy, long long bf16_n, const float* skip_flag, void* stream);
 
 /* ---- measurement hooks used by bench.py -------------------------------------------------------------------------- */
 /* ----------------------------------------------------------------------------------------------------------------
@@ -325,6 +336,9 @@ long long tpdm_launch_count(int reset);
  * stop returns, per class, the summed device time (ms), the algorithmic FLOPs and the number of launches */
 int tpdm_profile_start(int max_records);
 int tpdm_profile_stop(double* ms, double* flops, long long* count, int n_classes);
+/* launches of the last tpdm_profile_stop that were left out because the device skipped them (a denoising step enqueued
+ * speculatively after the trajectory had ended, see tpdm_sample_step): they did no work and are credited no FLOPs */
+long long tpdm_profile_dropped(void);
 
 /* ---- unit entry points used by tests/ (one kernel each) ---------------------------------------------------------- */
 /* out = epilogue(A[batch][rows][K] (bf16) . W[N][K]^T (bf16)); epi: 0 bias->bf16, 1 bias->f32, 2 bias+gelu->bf16,

@@ -545,7 +545,7 @@ class OraclePipeline(nn.Module):
             sigma = sigma_next
         stack = lambda xs: torch.stack([torch.stack(x) for x in xs])
         sigmas, logprobs, alphas, betas = stack(sigmas), stack(logprobs), stack(alphas), stack(betas)
-        prob_masks = stack(prob_masks).bool()
+        prob_masks = stack(prob_masks).bool().to(logprobs.device)   # the reference builds the mask entries on the host (:583,:588)
         logprobs = torch.masked_fill(logprobs, prob_masks, 1.0)                                       # :621
         hist = torch.stack(hist, dim=1)                                                               # (B, T, C, h, w)
         last_valid = torch.stack([torch.where(~prob_masks[i])[0][-1] for i in range(batch_size)])     # :647
@@ -573,14 +573,14 @@ class OraclePipeline(nn.Module):
             for i, (alpha, beta) in enumerate(tp):
                 sigma_next[i] = fix_sigmas[i][step]
                 if sigma[i] < self.min_sigma:
-                    logprobs[i].append(torch.zeros((), dtype=tp.dtype)); masks[i].append(torch.tensor(1))
+                    logprobs[i].append(torch.zeros((), dtype=tp.dtype, device=tp.device)); masks[i].append(torch.tensor(1))
                     continue
                 ratio = sigma_next[i] / sigma[i] if self.relative else sigma[i] - sigma_next[i]
                 ratio = torch.clamp(ratio, min=self.epsilon, max=1 - self.epsilon)
                 logprobs[i].append(beta_log_prob(alpha, beta, ratio)); masks[i].append(torch.tensor(0))
             sigma = sigma_next
         lp = torch.stack([torch.stack(x) for x in logprobs])
-        mk = torch.stack([torch.stack(x) for x in masks]).bool()
+        mk = torch.stack([torch.stack(x) for x in masks]).bool().to(lp.device)
         return {"logprobs": torch.masked_fill(lp, mk, 1.0)}
 
 

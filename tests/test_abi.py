@@ -34,7 +34,7 @@ def test_header_symbols_are_exported(lib):
 def test_abi_version_and_struct_sizes(lib):
     from tpdm_b200 import _lib as L
 
-    assert lib.tpdm_abi_version() == 2
+    assert lib.tpdm_abi_version() == 3
     assert C.sizeof(L.TpdmConfig) == 13 * 4 + 3 * 4 + 8          # 64 bytes, the uint64 mask is naturally aligned
     assert C.sizeof(L.TpdmBlockWeights) == 26 * 8
     assert C.sizeof(L.TpdmWeights) == (17 + 1 + 12) * 8

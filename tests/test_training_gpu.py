@@ -82,9 +82,11 @@ def test_ppo_clip_loss_and_dz_match_restated_trainer_math():
     f = lambda t: t.detach().float().contiguous()
     out_lp, dz, stats = torch.empty(mb, T, device="cuda"), torch.empty(mb * T, 2, device="cuda"), torch.empty(4, device="cuda")
     ab32, sig32, old32, adv32 = f(ab), f(sig), f(old_lp), f(adv)      # keep the fp32 copies alive across the async launch
-    L.check(lib.tpdm_ppo_clip_loss(L.ptr(ab32), L.ptr(sig32), L.ptr(old32), L.ptr(adv32), mb, T, min_sigma, 1e-3, 1, 0.2, 1.0,
-                                   L.ptr(out_lp), L.ptr(dz), L.ptr(stats), None))
+    tail = torch.full((2,), 7.0, device="cuda")
+    L.check(lib.tpdm_ppo_clip_loss(L.ptr(ab32), L.ptr(sig32), L.ptr(old32), L.ptr(adv32), mb, T, min_sigma, 1e-3, 1, 0, 0.2, 1.0,
+                                   L.ptr(out_lp), L.ptr(dz), L.ptr(stats), L.ptr(tail), None))
     torch.cuda.synchronize()
+    assert float(tail[0]) == float(stats[0]) and float(tail[1]) == 0.0      # {loss, non-finite flag} for the all-reduce tail
     assert torch.allclose(out_lp.double(), new_lp.detach(), atol=2e-4)
     assert abs(float(stats[0]) - float(loss)) < 2e-4 * max(1.0, abs(float(loss)))
     assert rel(dz, z.grad) < 2e-3
@@ -109,16 +111,142 @@ def test_adamw_step_matches_torch():
         torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
         opt.step()
         L.check(lib.tpdm_adamw_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.99, 1e-5, 0.01, 1.0, step, 1.0, L.ptr(sumsq),
-                                    L.ptr(copy), 1000, None))
+                                    L.ptr(copy), 1000, None, None))
         torch.cuda.synchronize()
         assert abs(float(sumsq.sqrt()) - float(g.norm())) < 1e-3 * float(g.norm())
         assert torch.allclose(p, ref_p.detach(), rtol=1e-5, atol=1e-6)
     assert torch.equal(copy, p[:1000].bfloat16())
     bad = torch.full((n,), float("nan"), device="cuda")      # NaN gradient: update skipped (rloo_trainer.py:518-520)
     before = p.clone()
-    L.check(lib.tpdm_adamw_step(L.ptr(p), L.ptr(bad), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.99, 1e-5, 0.01, 1.0, 4, 1.0, L.ptr(sumsq), None, 0, None))
+    L.check(lib.tpdm_adamw_step(L.ptr(p), L.ptr(bad), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.99, 1e-5, 0.01, 1.0, 4, 1.0, L.ptr(sumsq), None, 0, None, None))
     torch.cuda.synchronize()
     assert torch.equal(p, before)
+    # a raised non-finite-loss flag (summed over ranks by the gradient all-reduce) skips the step as well (rloo_trainer.py:497-500)
+    good, flag = torch.randn(n, device="cuda") * 0.001, torch.tensor([2.0], device="cuda")
+    L.check(lib.tpdm_adamw_step(L.ptr(p), L.ptr(good), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.99, 1e-5, 0.01, 1.0, 4, 1.0, L.ptr(sumsq), None, 0,
+                                L.ptr(flag), None))
+    torch.cuda.synchronize()
+    assert torch.equal(p, before)
+    flag.zero_()
+    L.check(lib.tpdm_adamw_step(L.ptr(p), L.ptr(good), L.ptr(m), L.ptr(v), n, 1e-3, 0.9, 0.99, 1e-5, 0.01, 1.0, 4, 1.0, L.ptr(sumsq), None, 0,
+                                L.ptr(flag), None))
+    torch.cuda.synchronize()
+    assert not torch.equal(p, before)
+
+
+@pytest.mark.parametrize("prediction_type,relative", [("alpha_beta", True), ("mode_concentration", True), ("alpha_beta", False)])
+def test_beta_logprob_and_dz_match_autograd(prediction_type, relative):
+    """tpdm_beta_logprob / the PPO kernel against autograd through the restated log-prob, incl. the mode_concentration
+    transform (modeling_sd3_pnt.py:559-563) the rollout applies: replay and PPO gradient must score the SAME distribution."""
+    from oracle import sd3_oracle as O
+    from tpdm_b200 import _lib as L
+
+    lib = L.load()
+    torch.manual_seed(4)
+    mb, T, min_sigma, eps = 5, 6, 0.02, 1e-3
+    tpm_eps = 1.0 if prediction_type == "alpha_beta" else 0.0
+    z = torch.randn(mb * T, 2, device="cuda", dtype=torch.float64) * 0.3
+    if prediction_type == "mode_concentration":
+        z[:, 0] = z[:, 0] * 0.5 - 0.6          # mode = exp(z0) in (0, 1)
+        z[:, 1] = z[:, 1] + 2.5                # concentration = exp(z1) > 2
+    z.requires_grad_(True)
+    p = torch.exp(z) + tpm_eps
+    p1, p2 = p[:, 0].reshape(mb, T), p[:, 1].reshape(mb, T)
+    a, b = (p1, p2) if prediction_type == "alpha_beta" else (p1 * (p2 - 2) + 1, (1 - p1) * (p2 - 2) + 1)
+    if relative:
+        sig = torch.cumprod(torch.rand(mb, T, device="cuda", dtype=torch.float64) * 0.4 + 0.3, dim=1)
+    else:
+        sig = 1.0 - torch.cumsum(torch.rand(mb, T, device="cuda", dtype=torch.float64) * 0.25, dim=1).clamp(max=0.999)
+    prev = torch.cat([torch.ones(mb, 1, device="cuda", dtype=torch.float64), sig[:, :-1]], 1)
+    mask = prev < min_sigma
+    r = torch.clamp(sig / prev if relative else prev - sig, eps, 1 - eps)
+    lp_ref = torch.where(mask, torch.ones_like(r), O.beta_log_prob(a, b, r))
+    w = torch.randn(mb, T, device="cuda", dtype=torch.float64)
+    (lp_ref * w).sum().backward(retain_graph=True)
+    f = lambda t: t.detach().float().contiguous()
+    ab32, sig32 = f(p), f(sig)
+    lp, dlp = torch.empty(mb, T, device="cuda"), torch.empty(mb * T, 2, device="cuda")
+    L.check(lib.tpdm_beta_logprob(L.ptr(ab32), L.ptr(sig32), mb, T, min_sigma, eps, int(relative), 0 if prediction_type == "alpha_beta" else 1,
+                                  tpm_eps, L.ptr(lp), L.ptr(dlp), None))
+    torch.cuda.synchronize()
+    assert torch.allclose(lp.double(), lp_ref.detach(), atol=3e-4, rtol=1e-5)
+    assert rel(dlp * f(w).reshape(-1, 1), z.grad) < 2e-3
+    # the PPO kernel applies the same transform (ADVICE r1: it used the raw head outputs)
+    z.grad = None
+    old_lp = (lp_ref.detach() + 0.1 * torch.randn(mb, T, device="cuda", dtype=torch.float64)).masked_fill(mask, 1.0)
+    adv = torch.randn(mb, device="cuda", dtype=torch.float64)
+    loss = O.ppo_clip_loss(lp_ref, old_lp, adv, 0.2)
+    loss.backward()
+    out_lp, dz, stats = torch.empty(mb, T, device="cuda"), torch.empty(mb * T, 2, device="cuda"), torch.empty(4, device="cuda")
+    old32, adv32 = f(old_lp), f(adv)
+    L.check(lib.tpdm_ppo_clip_loss(L.ptr(ab32), L.ptr(sig32), L.ptr(old32), L.ptr(adv32), mb, T, min_sigma, eps, int(relative),
+                                   0 if prediction_type == "alpha_beta" else 1, 0.2, tpm_eps, L.ptr(out_lp), L.ptr(dz), L.ptr(stats), None, None))
+    torch.cuda.synchronize()
+    assert abs(float(stats[0]) - float(loss)) < 3e-4 * max(1.0, abs(float(loss)))
+    assert rel(dz, z.grad) < 2e-3
+
+
+def test_wrapper_logprobs_is_differentiable_like_the_reference():
+    """rloo_trainer.py:485-501 on the drop-in: new_logprobs = model.logprobs(...); loss.backward() deposits time_predictor.*.grad.
+    The gradients equal autograd through the fp32 oracle TimePredictor on the same recorded inputs."""
+    from oracle import sd3_oracle as O
+    from tpdm_b200.modeling_sd3_pnt import SD3PredictNextTimeStepModelRLOOWrapper
+
+    tiny = dict(sample_size=32, patch_size=2, in_channels=16, num_layers=2, attention_head_dim=96, num_attention_heads=4,
+                joint_attention_dim=4096, caption_projection_dim=384, pooled_projection_dim=2048, out_channels=16, pos_embed_max_size=96)
+    torch.manual_seed(31)
+    wrapper = SD3PredictNextTimeStepModelRLOOWrapper(transformer_config=tiny, torch_dtype=torch.float32, device="cuda", min_sigma=0.05,
+                                                     max_inference_steps=6)
+    tp = wrapper.agent_model.time_predictor
+    with torch.no_grad():
+        tp.fc2.weight.mul_(10)
+        tp.fc1.weight.mul_(4)
+        tp.conv1.weight.copy_(tp.conv1.weight.bfloat16().float())        # tensor cores read conv1 in bf16
+    assert all(p.requires_grad for p in tp.parameters())
+    g = torch.Generator().manual_seed(5)
+    mk = lambda *s: torch.randn(*s, generator=g).cuda()
+    data = dict(prompt_embeds=mk(3, 333, 4096), negative_prompt_embeds=mk(3, 333, 4096), pooled_prompt_embeds=mk(3, 2048),
+                negative_pooled_prompt_embeds=mk(3, 2048), latents=mk(3, 16, 32, 32), predict=False, generator=torch.Generator().manual_seed(9))
+    outputs = wrapper.sample(dict(data))
+    old = outputs["logprobs"]
+    assert not old.requires_grad and outputs["hidden_states_combineds"].shape[:2] == old.shape
+    # micro-batch subset exactly as the trainer does (:480-485)
+    idx = torch.tensor([2, 0], device="cuda")
+    mb_out = wrapper.subset_outputs(outputs, idx)
+    new = wrapper.logprobs(None, mb_out)
+    assert new.requires_grad and new.shape == (2, old.shape[1])
+    assert float((new.detach() - old[idx]).abs().max()) < 5e-3          # same parameters: the replay reproduces the rollout
+    adv = torch.tensor([0.7, -1.3], device="cuda")
+    ratio = torch.exp(new.sum(1) - old[idx].sum(1))
+    loss = torch.max(-adv * ratio, -adv * torch.clamp(ratio, 0.8, 1.2)).mean()
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in tp.named_parameters()}
+    assert all(gr is not None and torch.isfinite(gr).all() for gr in grads.values())
+    # the same through autograd on the oracle head
+    ora = O.OracleTimePredictor(128, 768).cuda()
+    ora.load_state_dict(tp.state_dict())
+    pipe = O.OraclePipeline(O.tiny_config(), min_sigma=0.05)
+    pipe.time_predictor = ora                                            # trainable copy of the drop-in's head
+    ref_new = pipe.only_predict_logprobs(mb_out["sigmas"].float(), mb_out["hidden_states_combineds"].float(), mb_out["tembs"].float())["logprobs"]
+    ref_ratio = torch.exp(ref_new.sum(1) - old[idx].sum(1))
+    torch.max(-adv * ref_ratio, -adv * torch.clamp(ref_ratio, 0.8, 1.2)).mean().backward()
+    for name, p in ora.named_parameters():
+        tol = 2e-2 if name.startswith("conv1") else 1e-2
+        assert rel(grads[name], p.grad) < tol, (name, rel(grads[name], p.grad))
+    # gradient accumulation over a second micro-batch adds up (grads are deposited, not overwritten)
+    new2 = wrapper.logprobs(None, wrapper.subset_outputs(outputs, torch.tensor([1], device="cuda")))
+    new2.sum().backward()
+    assert rel(tp.fc2.bias.grad, grads["fc2.bias"]) > 1e-3
+    # torch.optim on the module parameters moves the native path (the packed copies are refreshed from the module)
+    opt = torch.optim.AdamW(tp.parameters(), lr=1e-2)
+    opt.step()
+    new3 = wrapper.logprobs(None, mb_out)
+    assert float((new3.detach() - new.detach()).abs().max()) > 1e-4
+    # a stale backward is refused instead of using overwritten activations
+    a = wrapper.logprobs(None, mb_out)
+    wrapper.logprobs(None, mb_out)
+    with pytest.raises(RuntimeError):
+        a.sum().backward()
 
 
 def test_rloo_update_end_to_end_tiny():
@@ -152,6 +280,47 @@ def test_rloo_update_end_to_end_tiny():
     assert torch.equal(t_before, w.agent_model.transformer.proj_out.weight)
     out = w.sample(dict(data, predict=True))
     assert torch.isfinite(out["latents"]).all()
+
+
+def test_nonfinite_loss_rides_the_gradient_buffer_and_skips_the_step():
+    """rloo_trainer.py:497-500 / 516-523: a NaN / Inf loss must not reach the optimizer.  The flag is the element right behind the
+    gradients in the ONE buffer that is all-reduced, and the fused AdamW reads it on the device."""
+    ora, tp, tr, x, temb = _pair(256, 16, 6)
+    mb, T = 2, 3
+    xn = x.permute(0, 2, 3, 1).contiguous().bfloat16().reshape(mb, T, 16, 16, 256)
+    tm = temb.reshape(mb, T, 128)
+    sig = torch.tensor([[0.7, 0.5, 0.3], [0.8, 0.6, 0.2]], device="cuda")
+    old = torch.zeros(mb, T, device="cuda")
+    assert tr.reduce_buf.data_ptr() == tr.grads.data_ptr() and tr.tail.data_ptr() == tr.grads.data_ptr() + 4 * tr.grads.numel()
+    before = tr.params.clone()
+    good = tr.ppo_update(sig, old, xn, tm, torch.tensor([0.5, -0.5], device="cuda"), min_sigma=0.01)
+    assert float(good["nonfinite"]) == 0.0 and torch.isfinite(good["loss"]) and not torch.equal(tr.params, before)
+    assert float(good["loss"]) == float(good["local_loss"])                    # world size 1: the tail carries this rank's loss
+    mid = tr.params.clone()
+    bad = tr.ppo_update(sig, old, xn, tm, torch.tensor([float("nan"), 1.0], device="cuda"), min_sigma=0.01)
+    assert float(bad["nonfinite"]) == 1.0 and float(bad["loss"]) == 0.0       # the NaN itself is kept out of the sum
+    assert torch.equal(tr.params, mid)                                         # update skipped on the device
+    again = tr.ppo_update(sig, old, xn, tm, torch.tensor([0.5, -0.5], device="cuda"), min_sigma=0.01)
+    assert float(again["nonfinite"]) == 0.0 and not torch.equal(tr.params, mid)
+
+
+def test_successive_rollouts_draw_independent_schedules():
+    """the Beta draws of predict=False must consume generator state like beta_dist.sample() (:569) does."""
+    from tpdm_b200.modeling_sd3_pnt import SD3PredictNextTimeStepModel
+
+    tcfg = dict(sample_size=32, num_layers=2, attention_head_dim=96, num_attention_heads=4, caption_projection_dim=384, pos_embed_max_size=96)
+    torch.manual_seed(5)
+    model = SD3PredictNextTimeStepModel(transformer_config=tcfg, torch_dtype=torch.float32, device="cuda")
+    g = torch.Generator().manual_seed(0)
+    kw = dict(prompt_embeds=torch.randn(2, 333, 4096, generator=g).cuda(), negative_prompt_embeds=torch.randn(2, 333, 4096, generator=g).cuda(),
+              pooled_prompt_embeds=torch.randn(2, 2048, generator=g).cuda(), negative_pooled_prompt_embeds=torch.randn(2, 2048, generator=g).cuda(),
+              latents=torch.randn(2, 16, 32, 32, generator=g).cuda(), max_inference_steps=5, predict=False)
+    gen = torch.Generator().manual_seed(42)
+    a = model(**kw, generator=gen)
+    b = model(**kw, generator=gen)                       # same generator, second call: new draws
+    assert not torch.equal(a.sigmas, b.sigmas)
+    c = model(**kw, generator=torch.Generator().manual_seed(42))
+    assert torch.equal(a.sigmas, c.sigmas)               # same generator state: same draws
 
 
 @pytest.mark.parametrize("relative,mean_kl", [(True, False), (False, True)])

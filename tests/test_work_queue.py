@@ -37,6 +37,10 @@ def _worker(rank, world, port, lengths, out_q):
 
     mine = sample_prompts(fake_trajectory, len(lengths), dynamic=True, name="q1")
     merged = gather_results(mine)
+    # a second queue of the same name in the same process group starts from zero (its own store key)
+    again = gather_results(sample_prompts(lambda i: {"steps": 1, "rank": rank}, 5, dynamic=True, name="q1"))
+    if rank == 0:
+        assert sorted(again) == [0, 1, 2, 3, 4]
     worst = max_over_ranks(busy[0])
     dist.barrier()
     if rank == 0:
@@ -70,4 +74,6 @@ def test_dynamic_queue_world_size_2():
 def test_queue_without_process_group():
     q = PromptQueue(3)
     assert list(q) == [0, 1, 2] and q.claim() is None
+    q2 = PromptQueue(2)
+    assert q2.key != q.key and list(q2) == [0, 1]
     assert static_shard(10, 1, 4) == [1, 5, 9]

@@ -239,6 +239,31 @@ if __name__ == "__main__":
             st = lib.tpdm_conv3x3_wgrad(L.ptr(dy.reshape(ns, M, g * g).contiguous()), L.ptr(xs), L.ptr(out), ns, g, Cc, M, None)
             torch.cuda.synchronize()
             print(f"wgrad ns={ns} g={g} C={Cc}: status={st} rel={rel(out, ref):.3e}", flush=True)
+    if which == "attn_lib":   # library bars for the joint attention of one SD3-medium block: (Bt, H, S, d) = (2, 24, 4429, 64), bf16
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        for (Bt, H, S, d) in ((2, 24, 4429, 64), (2, 24, 16717, 64), (32, 24, 1357, 64)):
+            flops = 4.0 * Bt * H * S * S * d
+            q, k, v = (torch.randn(Bt, H, S, d, device=dev, dtype=torch.bfloat16) for _ in range(3))
+            for name, be in (("torch SDPA cuDNN", SDPBackend.CUDNN_ATTENTION), ("torch SDPA flash", SDPBackend.FLASH_ATTENTION),
+                             ("torch SDPA mem-efficient", SDPBackend.EFFICIENT_ATTENTION)):
+                try:
+                    with sdpa_kernel(be):
+                        ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), 20)
+                    print(f"{name:26s} Bt={Bt} H={H} S={S} d={d}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TFLOP/s", flush=True)
+                except Exception as e:
+                    print(f"{name:26s} Bt={Bt} H={H} S={S} d={d}: unavailable ({str(e).splitlines()[0][:90]})", flush=True)
+            try:
+                from flash_attn import flash_attn_func
+                qf, kf, vf = (t.transpose(1, 2).contiguous() for t in (q, k, v))
+                ms = timeit(lambda: flash_attn_func(qf, kf, vf), 20)
+                print(f"{'flash_attn 2 (mma.sync)':26s} Bt={Bt} H={H} S={S} d={d}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TFLOP/s", flush=True)
+            except Exception as e:
+                print(f"flash_attn unavailable ({str(e).splitlines()[0][:90]})", flush=True)
+            qkv = torch.randn(Bt, S, 3, H, d, device=dev).bfloat16().contiguous()
+            out = torch.zeros(Bt, S, H, d, device=dev, dtype=torch.bfloat16)
+            ms = timeit(lambda: lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, 64, d, 0, None), 20)
+            print(f"{'tpdm joint_attention':26s} Bt={Bt} H={H} S={S} d={d}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TFLOP/s", flush=True)
+            del q, k, v, qkv, out
     if which == "attn_big":
         attn_case(2, 4429, 24, 64)
         attn_case(2, 4429, 24, 64)

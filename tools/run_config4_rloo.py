@@ -61,7 +61,7 @@ def main():
         new_lp, dz, stats = torch.empty(mb, T, device=dev), torch.empty(mb * T, 2, device=dev), torch.empty(4, device=dev)
         abv = trainer.forward(x[idx].reshape(-1, 32, 32, 3072), out["tembs"][idx].reshape(-1, 1536))
         sig, old, a = out["sigmas"][idx].float().contiguous(), out["logprobs"][idx].float().contiguous(), adv[idx].float().contiguous()
-        L.check(lib.tpdm_ppo_clip_loss(L.ptr(abv), L.ptr(sig), L.ptr(old), L.ptr(a), mb, T, 0.01, 1e-3, 1, 0.2, 1.0, L.ptr(new_lp), L.ptr(dz), L.ptr(stats), L.stream_ptr()))
+        L.check(lib.tpdm_ppo_clip_loss(L.ptr(abv), L.ptr(sig), L.ptr(old), L.ptr(a), mb, T, 0.01, 1e-3, 1, 0, 0.2, 1.0, L.ptr(new_lp), L.ptr(dz), L.ptr(stats), None, L.stream_ptr()))
         trainer.backward(dz)
         local_g = trainer.grads.clone()
         gathered = [torch.empty_like(local_g) for _ in range(world)]

@@ -101,11 +101,14 @@ EXPORTS = {
     "tpdm_vae_decode": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, vp, vp, vp]),
     "tpdm_rollout_shaping": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
                                        vp, vp, vp, vp, vp]),
-    "tpdm_ppo_clip_loss": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float, vp, vp, vp, vp]),
+    "tpdm_ppo_clip_loss": (C.c_int, [vp, vp, vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_float, vp, vp, vp,
+                                     vp, vp]),
+    "tpdm_beta_logprob": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, vp, vp, vp]),
     "tpdm_adamw_step": (C.c_int, [vp, vp, vp, vp, C.c_longlong, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int,
-                                  C.c_float, vp, vp, C.c_longlong, vp]),
+                                  C.c_float, vp, vp, C.c_longlong, vp, vp]),
     "tpdm_launch_count": (C.c_longlong, [C.c_int]),
     "tpdm_profile_start": (C.c_int, [C.c_int]),
+    "tpdm_profile_dropped": (C.c_longlong, []),
     "tpdm_profile_stop": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.c_int]),
     "tpdm_gemm_bf16": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
     "tpdm_joint_attention": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
@@ -129,7 +132,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if lib.tpdm_abi_version() != 2:
+        if lib.tpdm_abi_version() != 3:
             raise RuntimeError("libtpdm_b200.so ABI version mismatch")
         _lib = lib
     return _lib

@@ -54,5 +54,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines, sources=None) -> str:
+    """Diagnostic build: the whole library with extra -D flags into tpdm_b200/_build/libtpdm_<name>.so (load it by setting
+    TPDM_B200_LIB).  Used for the instrumented attention kernel (tools/attn_trace.py) and kernel experiments."""
+    obj_dir = os.path.join(HERE, "_build", name)
+    os.makedirs(obj_dir, exist_ok=True)
+    lib = os.path.join(HERE, "_build", f"libtpdm_{name}.so")
+    procs, objs = [], []
+    for src in SOURCES:
+        o = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        objs.append(o)
+        flags = [f"-D{d}" for d in defines] if (sources is None or src in sources) else []
+        base = os.path.join(HERE, "_build", src.replace(".cu", ".o"))
+        if not flags and os.path.exists(base):      # untouched translation unit: reuse the product object
+            objs[-1] = base
+            continue
+        procs.append((src, subprocess.Popen([NVCC, *FLAGS, *flags, "-c", os.path.join(CSRC, src), "-o", o], stdout=subprocess.PIPE,
+                                            stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(f"--- nvcc {src} failed ---\n{out}\n")
+            raise RuntimeError("nvcc failed")
+    subprocess.check_call([NVCC, "-shared", "-o", lib, *objs, "-lcudart"])
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2].split(","), ["attention_tcgen05.cu"]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -56,6 +56,18 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #endif
 constexpr int kPolyEvery = TPDM_POLY_EVERY;
 
+// -DTPDM_ATTN_TRACE: clock64() time stamps of one CTA's softmax warp 4 (role 0, 8 slots per half-tile) and of the two MMA-issuing
+// warps (roles 1 and 2, 4 slots per half-tile), read back with tpdm_attn_trace_read (tools/attn_trace.py).  Diagnostic builds only.
+#ifdef TPDM_ATTN_TRACE
+__device__ long long g_attn_trace[3][2048];
+#define ATRACE(role, idx)                                                                       \
+  do {                                                                                          \
+    if (trace_on && lane == 0 && (idx) < 2048) g_attn_trace[role][idx] = clock64();             \
+  } while (0)
+#else
+#define ATRACE(role, idx)
+#endif
+
 template <int DP>
 struct AttnSmem {
   static constexpr int kTile = kQT * DP * 2;  // bytes of one Q / K / V tile
@@ -94,6 +106,9 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   const int q0 = qt * kQT;
   const int n_kv = (A.S + kKT - 1) / kKT;
   const int n_half = (A.S + kHT - 1) / kHT;
+#ifdef TPDM_ATTN_TRACE
+  const bool trace_on = blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 0;
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&A.tmQ);
@@ -162,9 +177,11 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
     // half-tile i lives in K/V smem tile t = i/2 (ring stage t % 2, ring phase (t/2) & 1), rows [64 (i&1), +64)
     auto issue_qk = [&](int i) {
       const int t = i >> 1, hf = i & 1, stage = t % kKVStages;
+      ATRACE(1, 4 * i);
       if (hf == 0) mbar_wait(&k_full[stage], (t / kKVStages) & 1);
       if (i >= 2) mbar_wait(&s_free[i & 1], ((i - 2) >> 1) & 1);  // softmax(i-2) has read S[i&1]
       tc_fence_after();
+      ATRACE(1, 4 * i + 1);
       if (lane == 0) {
         const uint32_t k_base = smem_u32(smem + L::kKOff + stage * L::kTile) + hf * (kHT * 128);
         const uint32_t s_tmem = tmem_base + L::kSCol + (i & 1) * kHT;
@@ -177,13 +194,16 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
         umma_commit(&s_full[i & 1]);
         if (hf == 1 || i == n_half - 1) umma_commit(&k_empty[stage]);
       }
+      ATRACE(1, 4 * i + 2);
       __syncwarp();
     };
     auto issue_pv = [&](int i) {
       const int t = i >> 1, hf = i & 1, stage = t % kKVStages;
+      ATRACE(2, 4 * i);
       mbar_wait(&p_full[i & 1], (i >> 1) & 1);
       if (hf == 0) mbar_wait(&v_full[stage], (t / kKVStages) & 1);
       tc_fence_after();
+      ATRACE(2, 4 * i + 1);
       if (lane == 0) {
         const uint32_t v_base = smem_u32(smem + L::kVOff + stage * L::kTile) + hf * (kHT * 128);
         const uint32_t p_tmem = tmem_base + L::kPCol + (i & 1) * (kHT / 2);
@@ -197,6 +217,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
         umma_commit(&pv_done[i & 1]);
         if (hf == 1 || i == n_half - 1) umma_commit(&v_empty[stage]);
       }
+      ATRACE(2, 4 * i + 2);
       __syncwarp();
     };
 
@@ -278,9 +299,17 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       const uint32_t s_tmem = tmem_base + lane_off + L::kSCol + bb * kHT;
       const uint32_t p_tmem = tmem_base + lane_off + L::kPCol + bb * (kHT / 2);
       const int valid = A.S - i * kHT;  // keys valid in this half-tile (>= 1)
+#ifdef TPDM_ATTN_TRACE
+      const bool tr4 = trace_on && warp == 4;
+#define STRACE(e) do { if (tr4 && lane == 0 && 8 * i + (e) < 2048) g_attn_trace[0][8 * i + (e)] = clock64(); } while (0)
+#else
+#define STRACE(e)
+#endif
+      STRACE(0);
       mbar_wait(&s_full[bb], (i >> 1) & 1);
       if (i >= 2) mbar_wait(&pv_done[bb], ((i - 2) >> 1) & 1);  // P(i-2) V done: P[bb] may be overwritten
       tc_fence_after();
+      STRACE(1);
       if (__any_sync(0xffffffffu, need_pending)) {
         // every P V issued so far must have drained before O is touched (P(i-1) V is the newest; the MMAs retire in order)
         mbar_wait(&pv_done[bb ^ 1], ((i - 1) >> 1) & 1);
@@ -301,18 +330,23 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
         uint32_t va[32], vb[32];
         tmem_ld_32x32(s_tmem, va);
         tmem_wait_ld();
+        STRACE(2);
         tmem_ld_32x32(s_tmem + 32, vb);
         exp_chunk(va, p_tmem, negm2, true);
+        STRACE(3);
         tmem_wait_ld();
+        STRACE(4);
         exp_chunk(vb, p_tmem + 16, negm2, true);
         float l_lo, l_hi;
         unpack_f32x2(l2, l_lo, l_hi);
         const bool overflow = !(l_lo + l_hi < 1e37f);  // inf, NaN, or close enough to the bf16 / fp32 limit to round to inf
         if (!__any_sync(0xffffffffu, overflow)) {
           fast_ok = true;
+          STRACE(5);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&s_free[bb]);
+          STRACE(6);
         } else {
           l2 = l_save;  // S[bb] is still intact (s_free not signalled): redo on the exact route
         }
@@ -366,6 +400,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[bb]);
+      STRACE(7);
     }
     float l_lo, l_hi;
     unpack_f32x2(l2, l_lo, l_hi);
@@ -445,6 +480,12 @@ int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int 
   TPDM_TRY(encode_tmap_bf16(&op->tmV, base + static_cast<size_t>(2) * H * dp, 4, dims, strides, box));
   return 0;
 }
+
+#ifdef TPDM_ATTN_TRACE
+extern "C" int tpdm_attn_trace_read(long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(long long) * (n < 3 * 2048 ? n : 3 * 2048)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int attn_launch(const AttnOp* op_in, cudaStream_t stream) {
   AttnOp op_copy = *op_in;

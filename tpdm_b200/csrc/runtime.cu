@@ -53,7 +53,9 @@ struct Profiler {
   std::vector<cudaEvent_t> ev;
   std::vector<int> cls;
   std::vector<double> flops;
+  std::vector<const int*> skip;   // device skip flag the launch was made under (set_skip_flag), or null
   size_t n = 0;
+  long long dropped = 0;          // records of the last stop whose launch returned at once because its skip flag was set
   bool on = false;
 };
 Profiler g_prof;
@@ -63,6 +65,7 @@ void prof_begin(int cls, double flops, cudaStream_t s) {
   if (!g_prof.on || 2 * (g_prof.n + 1) > g_prof.ev.size()) return;
   g_prof.cls[g_prof.n] = cls;
   g_prof.flops[g_prof.n] = flops;
+  g_prof.skip[g_prof.n] = skip_flag();
   cudaEventRecord(g_prof.ev[2 * g_prof.n], s);
 }
 void prof_end(cudaStream_t s) {
@@ -136,6 +139,8 @@ extern "C" long long tpdm_launch_count(int reset) {
   return v;
 }
 
+extern "C" long long tpdm_profile_dropped(void) { return tpdm::g_prof.dropped; }
+
 extern "C" int tpdm_profile_start(int max_records) {
   using namespace tpdm;
   TPDM_CHECK(max_records > 0, TPDM_ERR_ARG, "tpdm_profile_start: max_records must be positive");
@@ -146,7 +151,9 @@ extern "C" int tpdm_profile_start(int max_records) {
   }
   g_prof.cls.assign(max_records, 0);
   g_prof.flops.assign(max_records, 0.0);
+  g_prof.skip.assign(max_records, nullptr);
   g_prof.n = 0;
+  g_prof.dropped = 0;
   g_prof.on = true;
   return 0;
 }
@@ -157,7 +164,23 @@ extern "C" int tpdm_profile_stop(double* ms, double* flops, long long* count, in
   g_prof.on = false;
   for (int c = 0; c < n_classes; ++c) ms[c] = flops[c] = 0.0, count[c] = 0;
   if (g_prof.n > 0) TPDM_CUDA_OK(cudaEventSynchronize(g_prof.ev[2 * g_prof.n - 1]));
+  // A launch made under a skip flag that reads 1 now was a speculatively enqueued step the device skipped (the flags are
+  // write-once per trajectory: all_done[k] / idle_flag go 0 -> 1 and stay).  Such records carry no work: they are dropped, so
+  // neither their algorithmic FLOPs nor their (~0) time reach the per-class sums.
+  const int* last_ptr = nullptr;
+  int last_val = 0;
+  g_prof.dropped = 0;
   for (size_t i = 0; i < g_prof.n; ++i) {
+    if (g_prof.skip[i] != nullptr) {
+      if (g_prof.skip[i] != last_ptr) {
+        last_ptr = g_prof.skip[i];
+        TPDM_CUDA_OK(cudaMemcpy(&last_val, last_ptr, sizeof(int), cudaMemcpyDeviceToHost));
+      }
+      if (last_val != 0) {
+        ++g_prof.dropped;
+        continue;
+      }
+    }
     float t = 0.f;
     TPDM_CUDA_OK(cudaEventElapsedTime(&t, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
     const int c = g_prof.cls[i];

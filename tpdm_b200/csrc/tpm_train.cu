@@ -158,10 +158,38 @@ __device__ double digamma_d(double x) {
   return r + log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f / 132.0))));
 }
 
+// Beta(alpha, beta).log_prob(r) and its derivatives with respect to the two fc2 outputs z (TimePredictor.forward ends in
+// p = exp(z) + eps, modeling_sd3_pnt.py:115, so dp/dz = p - eps).  prediction_type 0: (alpha, beta) = (p1, p2);
+// 1 ("mode_concentration", :559-563): alpha = p1 (p2 - 2) + 1, beta = (1 - p1)(p2 - 2) + 1, chain-ruled here so that the
+// rollout (schedule_kernel), the replay and the PPO gradient all use the same distribution.
+__device__ void beta_logprob_terms(double p1, double p2, double r, int prediction_type, double tpm_eps, double* lp, double* dz0, double* dz1) {
+  double A = p1, B = p2;
+  if (prediction_type != 0) {
+    A = p1 * (p2 - 2.0) + 1.0;
+    B = (1.0 - p1) * (p2 - 2.0) + 1.0;
+  }
+  *lp = (A - 1.0) * log(r) + (B - 1.0) * log1p(-r) + lgamma(A + B) - lgamma(A) - lgamma(B);
+  const double psi_ab = digamma_d(A + B);
+  const double dA = log(r) + psi_ab - digamma_d(A), dB = log1p(-r) + psi_ab - digamma_d(B);
+  if (prediction_type == 0) {
+    *dz0 = dA * (p1 - tpm_eps);
+    *dz1 = dB * (p2 - tpm_eps);
+  } else {
+    *dz0 = (dA - dB) * (p2 - 2.0) * (p1 - tpm_eps);
+    *dz1 = (dA * p1 + dB * (1.0 - p1)) * (p2 - tpm_eps);
+  }
+}
+
+// the ratio the replay scores (modeling_sd3_pnt.py:703-712): sigma_next / sigma, or sigma - sigma_next when not relative
+__device__ __forceinline__ float replay_ratio(float sigma, float sigma_next, int relative, float eps) {
+  const float r = relative ? sigma_next / sigma : sigma - sigma_next;
+  return fminf(fmaxf(r, eps), 1.f - eps);
+}
+
 struct PpoArgs {
   const float *alpha_beta, *sigmas, *old_logprobs, *advantages;
-  float *new_logprobs, *dz, *stats;
-  int mb, T, relative;
+  float *new_logprobs, *dz, *stats, *reduce_tail;
+  int mb, T, relative, prediction_type;
   float min_sigma, eps, cliprange, tpm_eps;
 };
 
@@ -177,10 +205,15 @@ __global__ void ppo_clip_kernel(const PpoArgs a) {
       const float sigma_next = a.sigmas[o];
       float lp = 1.0f;  // INVALID_LOGPROB for finished samples (modeling_sd3_pnt.py:721-724)
       if (!(sigma < a.min_sigma)) {
-        float r = a.relative ? sigma_next / sigma : sigma - sigma_next;
-        r = fminf(fmaxf(r, a.eps), 1.f - a.eps);
-        const double A = a.alpha_beta[2 * o], B = a.alpha_beta[2 * o + 1], R = r;
-        lp = static_cast<float>((A - 1.0) * log(R) + (B - 1.0) * log1p(-R) + lgamma(A + B) - lgamma(A) - lgamma(B));
+        double l, d0, d1;
+        beta_logprob_terms(a.alpha_beta[2 * o], a.alpha_beta[2 * o + 1], replay_ratio(sigma, sigma_next, a.relative, a.eps), a.prediction_type,
+                           a.tpm_eps, &l, &d0, &d1);
+        lp = static_cast<float>(l);
+        a.dz[2 * o] = static_cast<float>(d0);       // scaled by the loss coefficient below
+        a.dz[2 * o + 1] = static_cast<float>(d1);
+      } else {
+        a.dz[2 * o] = 0.f;
+        a.dz[2 * o + 1] = 0.f;
       }
       a.new_logprobs[o] = lp;
       sum_new += lp;
@@ -197,23 +230,10 @@ __global__ void ppo_clip_kernel(const PpoArgs a) {
     // d loss / d sum_new: through -A*ratio when that branch is the max, else through the clamp (zero outside the range)
     const bool inside = ratio >= 1.f - a.cliprange && ratio <= 1.f + a.cliprange;
     const float coef = (l1 >= l2 || inside) ? (-adv * ratio / a.mb) : 0.f;
-    sigma = 1.0f;
     for (int t = 0; t < a.T; ++t) {
       const int o = b * a.T + t;
-      const float sigma_next = a.sigmas[o];
-      float dza = 0.f, dzb = 0.f;
-      if (!(sigma < a.min_sigma)) {
-        float r = a.relative ? sigma_next / sigma : sigma - sigma_next;
-        r = fminf(fmaxf(r, a.eps), 1.f - a.eps);
-        const double A = a.alpha_beta[2 * o], B = a.alpha_beta[2 * o + 1], R = r;
-        const double psi_ab = digamma_d(A + B);
-        // alpha = exp(z0) + eps  ->  d alpha / d z0 = alpha - eps
-        dza = coef * static_cast<float>((log(R) + psi_ab - digamma_d(A)) * (A - a.tpm_eps));
-        dzb = coef * static_cast<float>((log1p(-R) + psi_ab - digamma_d(B)) * (B - a.tpm_eps));
-      }
-      a.dz[2 * o] = dza;
-      a.dz[2 * o + 1] = dzb;
-      sigma = sigma_next;
+      a.dz[2 * o] *= coef;
+      a.dz[2 * o + 1] *= coef;
     }
   }
   float vals[4] = {loss, clipped, kl, ratio_out};
@@ -226,6 +246,45 @@ __global__ void ppo_clip_kernel(const PpoArgs a) {
     float s = 0.f;
     for (int w = 0; w < (blockDim.x + 31) / 32; ++w) s += red[threadIdx.x][w];
     a.stats[threadIdx.x] = s;
+    if (threadIdx.x == 0 && a.reduce_tail) {
+      // rides behind the gradients in the flat all-reduce buffer (rloo_trainer.py:497-500: gather(loss), NaN / Inf guard)
+      a.reduce_tail[0] = isfinite(s) ? s : 0.f;
+      a.reduce_tail[1] = isfinite(s) ? 0.f : 1.f;
+    }
+  }
+}
+
+// only_predict_logprobs (modeling_sd3_pnt.py:670-726) after the TimePredictor: log-prob of the recorded ratio per (sample,
+// step), 1.0 at finished steps, and d logprob / d z for the autograd hook of the drop-in module
+struct LogprobArgs {
+  const float *alpha_beta, *sigmas;
+  float *logprobs, *dlp_dz;
+  int mb, T, relative, prediction_type;
+  float min_sigma, eps, tpm_eps;
+};
+
+__global__ void beta_logprob_kernel(const LogprobArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.mb) return;
+  float sigma = 1.0f;
+  for (int t = 0; t < a.T; ++t) {
+    const int o = b * a.T + t;
+    const float sigma_next = a.sigmas[o];
+    float lp = 1.0f, d0 = 0.f, d1 = 0.f;
+    if (!(sigma < a.min_sigma)) {
+      double l, g0, g1;
+      beta_logprob_terms(a.alpha_beta[2 * o], a.alpha_beta[2 * o + 1], replay_ratio(sigma, sigma_next, a.relative, a.eps), a.prediction_type,
+                         a.tpm_eps, &l, &g0, &g1);
+      lp = static_cast<float>(l);
+      d0 = static_cast<float>(g0);
+      d1 = static_cast<float>(g1);
+    }
+    a.logprobs[o] = lp;
+    if (a.dlp_dz) {
+      a.dlp_dz[2 * o] = d0;
+      a.dlp_dz[2 * o + 1] = d1;
+    }
+    sigma = sigma_next;
   }
 }
 
@@ -445,9 +504,11 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                                     long long n, float lr, float b1, float b2, float eps, float wd, float max_norm, float grad_scale,
                                                     float bc1, float bc2, const double* __restrict__ sumsq, bf16* __restrict__ bf16_copy,
-                                                    long long bf16_n) {
+                                                    long long bf16_n, const float* __restrict__ skip_flag) {
   const float norm = sqrtf(static_cast<float>(*sumsq));
-  const bool finite = isfinite(norm);  // NaN / Inf gradient: skip the update (rloo_trainer.py:518-520)
+  // NaN / Inf gradient norm, or a non-finite loss on ANY rank (flag summed by the gradient all-reduce): skip the update
+  // (rloo_trainer.py:497-500, 518-520)
+  const bool finite = isfinite(norm) && (skip_flag == nullptr || *skip_flag == 0.f);
   const float clip = (max_norm > 0.f && norm > max_norm) ? max_norm / (norm + 1e-6f) : 1.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
     float w = p[i];
@@ -682,12 +743,26 @@ int tpdm_tpm_train_backward(tpdm_tpm_trainer* t, const float* dz, void* stream) 
   return 0;
 }
 
+int tpdm_beta_logprob(const float* alpha_beta, const float* sigmas, int mb, int T, float min_sigma, float epsilon, int relative,
+                      int prediction_type, float tpm_epsilon, float* logprobs, float* dlp_dz, void* stream) {
+  TPDM_CHECK(alpha_beta && sigmas && logprobs, TPDM_ERR_ARG, "tpdm_beta_logprob: null argument");
+  TPDM_CHECK(mb > 0 && T > 0, TPDM_ERR_SHAPE, "tpdm_beta_logprob: empty input");
+  TPDM_CHECK(prediction_type == 0 || prediction_type == 1, TPDM_ERR_ARG, "tpdm_beta_logprob: prediction_type %d unknown", prediction_type);
+  LogprobArgs a{alpha_beta, sigmas, logprobs, dlp_dz, mb, T, relative, prediction_type, min_sigma, epsilon, tpm_epsilon};
+  beta_logprob_kernel<<<(mb + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  count_launch();
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int tpdm_ppo_clip_loss(const float* alpha_beta, const float* sigmas, const float* old_logprobs, const float* advantages, int mb, int T,
-                       float min_sigma, float epsilon, int relative, float cliprange, float tpm_epsilon, float* new_logprobs, float* dz,
-                       float* stats4, void* stream) {
+                       float min_sigma, float epsilon, int relative, int prediction_type, float cliprange, float tpm_epsilon,
+                       float* new_logprobs, float* dz, float* stats4, float* reduce_tail, void* stream) {
   TPDM_CHECK(alpha_beta && sigmas && old_logprobs && advantages && new_logprobs && dz && stats4, TPDM_ERR_ARG, "tpdm_ppo_clip_loss: null argument");
   TPDM_CHECK(mb > 0 && mb <= 1024 && T > 0, TPDM_ERR_SHAPE, "tpdm_ppo_clip_loss: micro-batch %d outside [1,1024]", mb);
-  PpoArgs a{alpha_beta, sigmas, old_logprobs, advantages, new_logprobs, dz, stats4, mb, T, relative, min_sigma, epsilon, cliprange, tpm_epsilon};
+  TPDM_CHECK(prediction_type == 0 || prediction_type == 1, TPDM_ERR_ARG, "tpdm_ppo_clip_loss: prediction_type %d unknown", prediction_type);
+  PpoArgs a{alpha_beta, sigmas, old_logprobs, advantages, new_logprobs, dz, stats4, reduce_tail, mb, T, relative, prediction_type,
+            min_sigma, epsilon, cliprange, tpm_epsilon};
   ppo_clip_kernel<<<1, ((mb + 31) / 32) * 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
@@ -712,7 +787,7 @@ int tpdm_rollout_shaping(const float* alphas, const float* betas, const float* s
 
 int tpdm_adamw_step(float* params, const float* grads, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                     float weight_decay, float max_grad_norm, int step, float grad_scale, double* scratch_sumsq, void* bf16_copy,
-                    long long bf16_n, void* stream) {
+                    long long bf16_n, const float* skip_flag, void* stream) {
   TPDM_CHECK(params && grads && m && v && scratch_sumsq, TPDM_ERR_ARG, "tpdm_adamw_step: null argument");
   TPDM_CHECK(n > 0 && step >= 1, TPDM_ERR_ARG, "tpdm_adamw_step: n and step must be positive");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -721,7 +796,7 @@ int tpdm_adamw_step(float* params, const float* grads, float* m, float* v, long 
   count_launch();
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step)), bc2 = 1.f - powf(beta2, static_cast<float>(step));
   adamw_kernel<<<592, 256, 0, s>>>(params, grads, m, v, n, lr, beta1, beta2, eps, weight_decay, max_grad_norm, grad_scale, bc1, bc2, scratch_sumsq,
-                                  reinterpret_cast<bf16*>(bf16_copy), bf16_copy ? bf16_n : 0);
+                                  reinterpret_cast<bf16*>(bf16_copy), bf16_copy ? bf16_n : 0, skip_flag);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
   return 0;

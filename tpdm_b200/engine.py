@@ -370,7 +370,7 @@ class Engine:
 
     def sample_queue(self, latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
                      slots: int, max_inference_steps: int, guidance_scale: float, ticket: Optional[torch.Tensor] = None,
-                     out_latents: Optional[torch.Tensor] = None, use_graph: bool = True):
+                     out_latents: Optional[torch.Tensor] = None, use_graph: bool = True, schedule: str = "fifo"):
         """Device-side prompt queue (``tpdm_queue_*``): all P prompts are resident, ``slots`` of them are in flight; a slot
         whose trajectory ends takes the next ticket on the device.  ``ticket`` (int32 device tensor of one element, zeroed by
         its owner) may be shared between GPUs, which then split one prompt list between them.  Returns device tensors:
@@ -378,6 +378,8 @@ class Engine:
         lib = L.load()
         P, Cc, h, w = latents.shape
         dev, f32 = self.device, torch.float32
+        if schedule != "fifo":
+            raise ValueError(f"unknown queue schedule {schedule!r} (tickets are handed out in prompt order: 'fifo')")
         if not 1 <= slots <= P:
             raise ValueError(f"slots must be in [1, {P}]")
         plan = self.plan(slots, True, h, prompt_embeds.shape[1], max_inference_steps)

@@ -28,6 +28,16 @@ SD3_MEDIUM_TRANSFORMER_CONFIG = dict(
     joint_attention_dim=4096, caption_projection_dim=1536, pooled_projection_dim=2048, out_channels=16, pos_embed_max_size=192)
 
 
+def _check_loaded(what: str, result, ignore_unexpected=()):
+    """``load_state_dict(strict=False)`` must not silently leave random-init weights behind (from_pretrained reports them)."""
+    missing = list(result.missing_keys)
+    unexpected = [k for k in result.unexpected_keys if not k.startswith(tuple(ignore_unexpected))] if ignore_unexpected else list(result.unexpected_keys)
+    if missing:
+        raise ValueError(f"{what} checkpoint is missing {len(missing)} tensors, e.g. {missing[:4]}")
+    if unexpected:
+        logger.warning("%s checkpoint has %d tensors this module does not use, e.g. %s", what, len(unexpected), unexpected[:4])
+
+
 def reshape_hidden_states_to_2d(hidden_states: torch.Tensor, height: int = 64, width: int = 64, patch_size: int = 2) -> torch.Tensor:
     """modeling_sd3_pnt.py:33-54 (a pure re-indexing; the CUDA path folds it into its store addresses instead)."""
     hidden_states = hidden_states.reshape(
@@ -151,12 +161,12 @@ class SD3PredictNextTimeStepModel(nn.Module):
             if vae_weights is not None and os.path.isfile(vae_weights):
                 from safetensors.torch import load_file
 
-                self.vae.load_state_dict(load_file(vae_weights), strict=False)
+                _check_loaded("vae", self.vae.load_state_dict(load_file(vae_weights), strict=False), ("encoder.", "quant_conv.", "post_quant_conv."))
         self.transformer = CustomSD3Transformer2DModel(**cfg, device=device, dtype=torch_dtype)
         if weights_file is not None and os.path.isfile(weights_file):
             from safetensors.torch import load_file
 
-            self.transformer.load_state_dict(load_file(weights_file), strict=False)
+            _check_loaded("transformer", self.transformer.load_state_dict(load_file(weights_file), strict=False))
         self.time_predictor = TimePredictor(
             conv_out_channels=128, in_channels=self.transformer.config.caption_projection_dim * 2, projection_dim=2,
             init_alpha=init_alpha, init_beta=init_beta, device=device, dtype=torch_dtype)
@@ -252,12 +262,16 @@ class SD3PredictNextTimeStepModel(nn.Module):
         ratios: Optional[torch.Tensor] = None,
         return_velocities: bool = False,
         output_type: str = "pil",
+        return_hidden_states: Optional[bool] = None,
     ) -> CustomDiffusionModelOutput:
         """Reference signature (modeling_sd3_pnt.py:447-463) + additions: ``output_type`` ("pil" as the reference's
         image_processor.postprocess, "uint8" device tensors (1, H, W, 3), "pt" fp32 (1, 3, H, W)) for the images and:
         ``ratios`` (B, max_inference_steps): Beta draws to inject when predict=False so that two implementations follow
         one trajectory; when omitted the draws are made on the device (the reference calls ``beta_dist.sample()``, :569),
-        seeded from ``generator``.  ``return_velocities`` records the per-step CFG velocity (parity tests)."""
+        seeded from ``generator``.  ``return_velocities`` records the per-step CFG velocity (parity tests).
+        ``return_hidden_states``: the reference always returns ``hidden_states_combineds`` (:553, 623, one 25 MB D2H copy per
+        sample and step); here they stay on the device and are recorded by default only for rollouts (predict=False), which is
+        what ``only_predict_logprobs`` replays -- pass True to get them for predict=True as well."""
         if prompt_embeds is None:
             prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = self.encode_prompt(
                 prompt=prompt, negative_prompt=negative_prompt, num_images_per_prompt=num_images_per_prompt)
@@ -276,12 +290,15 @@ class SD3PredictNextTimeStepModel(nn.Module):
             max_inference_steps = len(fix_sigmas[0])
         seed = 0
         if not predict and ratios is None:
+            # beta_dist.sample() (:569) consumes RNG state: draw the Philox seed of this call FROM the generator, so that a
+            # generator reused for several rollouts gives independent schedules (and the same generator state, the same ones)
             gen = generator[0] if isinstance(generator, (list, tuple)) else generator
-            seed = int(gen.initial_seed()) if gen is not None else int(torch.randint(0, 2**31 - 1, (1,)).item())
+            seed = int(torch.randint(0, 2**62, (1,), generator=gen, device=gen.device if gen is not None else "cpu").item())
         eng = self.get_engine()
         res = eng.sample(latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
                          max_inference_steps, float(guidance_scale), bool(predict), ratios=ratios, seed=seed,
-                         record_tpm_inputs=not predict, record_velocity=return_velocities)
+                         record_tpm_inputs=(not predict) if return_hidden_states is None else bool(return_hidden_states),
+                         record_velocity=return_velocities)
         out_dtype = latents.dtype
         prob_masks = res["prob_masks"]
         logprobs = torch.masked_fill(res["logprobs_raw"], prob_masks, 1.0)          # INVALID_LOGPROB (:615-621)
@@ -322,7 +339,7 @@ class SD3PredictNextTimeStepModel(nn.Module):
     @torch.no_grad()
     def sample_queue(self, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds, latents=None,
                      slots: int = 2, max_inference_steps: int = 28, guidance_scale: float = 7.0, generator=None, ticket=None,
-                     decode: bool = False, output_type: str = "pil", use_graph: bool = True):
+                     decode: bool = False, output_type: str = "pil", use_graph: bool = True, schedule: str = "fifo"):
         """Many prompts with different trajectory lengths on one GPU (BASELINE config 3): ``slots`` prompts are in flight, a
         finished one is replaced on the device from a ticket counter (which several GPUs may share).  Each prompt follows
         exactly the trajectory ``forward(..., predict=True)`` gives it with batch size 1.  Returns a
@@ -334,7 +351,7 @@ class SD3PredictNextTimeStepModel(nn.Module):
             latents = self.prepare_latents(P, self.transformer.config.in_channels, side, side, prompt_embeds.dtype, self.device, generator, None)
         res = self.get_engine().sample_queue(latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds,
                                              negative_pooled_prompt_embeds, int(slots), int(max_inference_steps), float(guidance_scale),
-                                             ticket=ticket, use_graph=use_graph)
+                                             ticket=ticket, use_graph=use_graph, schedule=schedule)
         images = []
         if decode and self.vae is not None and hasattr(self.vae, "decode_latents"):
             mine = (res["steps"] > 0).nonzero().flatten().tolist()
@@ -345,36 +362,47 @@ class SD3PredictNextTimeStepModel(nn.Module):
             device_steps=res["device_steps"])
 
     # ---------------------------------------------------------------------------------------------------------------
-    @torch.no_grad()
+    def _replay_trainer(self, grid: int, samples: int):
+        """TimePredictorTrainer (native forward with saved activations + backward) behind the differentiable replay."""
+        from .tpm_training import TimePredictorTrainer
+
+        tr = getattr(self, "_replay", None)
+        if tr is None or tr.g != grid or tr.max_samples < samples or tr.module is not self.time_predictor:
+            self._replay = None          # release the old workspace first
+            tr = self._replay = TimePredictorTrainer(self.time_predictor, grid, samples)
+        return tr
+
     def only_predict_logprobs(self, fix_sigmas: torch.Tensor, fix_hidden_states_combineds: torch.Tensor, fix_tembs: torch.Tensor):
-        """modeling_sd3_pnt.py:670-726 (forward replay; gradients w.r.t. the TPM are the next row of SURVEY section 8a)."""
+        """modeling_sd3_pnt.py:670-726.  With autograd enabled and a trainable ``time_predictor`` (the RLOO wrapper, :760-763) the
+        result carries a grad_fn whose backward is the native TimePredictor backward and deposits ``time_predictor.*.grad``, so
+        ``loss.backward()`` in the reference trainer (rloo_trainer.py:485-501) works on the drop-in; otherwise a plain replay."""
+        from . import _lib as L
+
         if fix_sigmas is None:
             raise ValueError("fix_sigmas must be provided")
         if fix_hidden_states_combineds is None:
             raise ValueError("fix_hidden_states_combineds must be provided")
-        eng = self.get_engine()
         device = self.device
         batch_size, steps = fix_sigmas.shape[:2]
-        fix_sigmas = fix_sigmas.to(device=device, dtype=torch.float32)
-        sigma = torch.ones(batch_size, dtype=torch.float32, device=device)
-        logprobs, masks = [], []
-        for step in range(steps):
-            ab = eng.tpm_forward(fix_hidden_states_combineds[:, step], fix_tembs[:, step])
-            alpha, beta = ab[:, 0], ab[:, 1]
-            if self.prediction_type == "mode_concentration":
-                alpha, beta = ab[:, 0] * (ab[:, 1] - 2) + 1, (1 - ab[:, 0]) * (ab[:, 1] - 2) + 1
-            sigma_next = fix_sigmas[:, step]
-            finished = sigma < self.min_sigma
-            ratio = sigma_next / sigma if self.relative else sigma - sigma_next
-            ratio = torch.clamp(torch.where(finished, torch.full_like(ratio, 0.5), ratio), min=self.epsilon, max=1 - self.epsilon)
-            lp = ((alpha - 1) * torch.log(ratio) + (beta - 1) * torch.log1p(-ratio)
-                  + torch.lgamma(alpha + beta) - torch.lgamma(alpha) - torch.lgamma(beta))
-            logprobs.append(torch.where(finished, torch.zeros_like(lp), lp))
-            masks.append(finished)
-            sigma = sigma_next
-        logprobs = torch.stack(logprobs, dim=1)
-        masks = torch.stack(masks, dim=1)
-        return {"logprobs": torch.masked_fill(logprobs, masks, 1.0)}
+        ptype = self.prediction_type
+        hcs = fix_hidden_states_combineds.to(device)                 # the reference keeps them on the CPU (:553, :689)
+        tembs = fix_tembs.to(device)
+        g = hcs.shape[-1]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.time_predictor.parameters()):
+            x_nhwc = hcs.permute(0, 1, 3, 4, 2)                      # a view of the NHWC storage forward() recorded
+            tr = self._replay_trainer(g, batch_size * steps)
+            lp = tr.logprobs(fix_sigmas, x_nhwc, tembs, self.min_sigma, self.epsilon, self.relative, ptype)
+            return {"logprobs": lp}
+        with torch.no_grad():
+            eng = self.get_engine()
+            ab = torch.stack([eng.tpm_forward(hcs[:, step], tembs[:, step]) for step in range(steps)], dim=1).contiguous()   # (B, T, 2)
+            sig = fix_sigmas.to(device=device, dtype=torch.float32).contiguous()
+            lp = torch.empty(batch_size, steps, device=device, dtype=torch.float32)
+            with torch.cuda.device(device):
+                L.check(L.load().tpdm_beta_logprob(L.ptr(ab), L.ptr(sig), batch_size, steps, float(self.min_sigma), float(self.epsilon),
+                                                   1 if self.relative else 0, 0 if ptype == "alpha_beta" else 1,
+                                                   float(self.time_predictor.epsilon), L.ptr(lp), None, L.stream_ptr()))
+        return {"logprobs": lp}
 
 
 class SD3PredictNextTimeStepModelRLOOWrapper(nn.Module):
@@ -487,7 +515,7 @@ class SD3PredictNextTimeStepModelRLOOWrapper(nn.Module):
             if isinstance(value, torch.Tensor):
                 subset[key] = value[micro_batch_inds]
             elif isinstance(value, list):
-                subset[key] = [value[i] for i in micro_batch_inds]
+                subset[key] = [value[i] for i in micro_batch_inds] if len(value) else []    # `images` is empty without a VAE
             elif isinstance(value, dict):
                 subset[key] = {k: v[micro_batch_inds] for k, v in value.items() if isinstance(v, torch.Tensor)}
             elif value is None:

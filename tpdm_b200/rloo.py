@@ -6,7 +6,6 @@ from __future__ import annotations
 
 from typing import Callable, Dict, List, Optional
 
-import numpy as np
 import torch
 
 from .tpm_training import TimePredictorTrainer
@@ -47,12 +46,20 @@ def rloo_advantages(rlhf_reward: torch.Tensor, rloo_k: int) -> torch.Tensor:
 
 
 def rloo_update(wrapper, trainer: TimePredictorTrainer, data: Dict, reward_fn: Callable, rloo_k: int = 2, num_ppo_epochs: int = 4,
-                micro_batch_size: int = 8, cliprange: float = 0.2, gamma: float = 0.97, kl_coef: float = 0.0, seed: int = 0) -> Dict:
+                micro_batch_size: int = 8, cliprange: float = 0.2, gamma: float = 0.97, kl_coef: float = 0.0, seed: int = 0,
+                generator: Optional[torch.Generator] = None) -> Dict:
     """`wrapper`: SD3PredictNextTimeStepModelRLOOWrapper; `data`: dict with the four embedding tensors (and optionally
-    'prompt'); `reward_fn(latents (B,C,h,w), outputs) -> (B,)` stands in for the reward model."""
+    'prompt'); `reward_fn(latents (B,C,h,w), outputs) -> (B,)` stands in for the reward model.  Randomness (initial noise, Beta
+    draws, micro-batch permutations) comes from ``generator``, or from one generator per trainer that is seeded with ``seed`` on
+    the FIRST update and then keeps advancing, so successive updates see independent rollouts (the reference's global RNG does
+    the same, rloo_trainer.py:133)."""
     agent = wrapper.agent_model
     data = wrapper.rloo_repeat(dict(data), rloo_k)
-    outputs = wrapper.sample({**data, "predict": False, "generator": torch.Generator().manual_seed(seed)})
+    if generator is None:
+        generator = getattr(trainer, "_rollout_generator", None)
+        if generator is None:
+            generator = trainer._rollout_generator = torch.Generator().manual_seed(seed)
+    outputs = wrapper.sample({**data, "predict": False, "generator": generator})
     prob_masks = outputs["prob_masks"]
     last_reward = reward_fn(outputs["latents"], outputs).float()
     shaped = shape_rollout(outputs, last_reward, relative=agent.relative, gamma=gamma, kl_coef=kl_coef, rloo_k=rloo_k)
@@ -60,13 +67,13 @@ def rloo_update(wrapper, trainer: TimePredictorTrainer, data: Dict, reward_fn: C
     B = scores.shape[0]
     x = outputs["hidden_states_combineds"].permute(0, 1, 3, 4, 2)     # back to the NHWC storage it is a view of
     logs: List[Dict] = []
-    rng = np.random.RandomState(seed)
     for _ in range(num_ppo_epochs):
-        perm = rng.permutation(B)
+        perm = torch.randperm(B, generator=generator).numpy()
         for s in range(0, B, micro_batch_size):
             idx = torch.as_tensor(perm[s: s + micro_batch_size], device=agent.device)
             st = trainer.ppo_update(outputs["sigmas"][idx], outputs["logprobs"][idx], x[idx], outputs["tembs"][idx], advantages[idx],
-                                    min_sigma=agent.min_sigma, cliprange=cliprange, epsilon=agent.epsilon, relative=agent.relative)
+                                    min_sigma=agent.min_sigma, cliprange=cliprange, epsilon=agent.epsilon, relative=agent.relative,
+                                    prediction_type=agent.prediction_type)
             logs.append({k: float(v) for k, v in st.items() if k != "new_logprobs"})
     trainer.sync_to_module()
     return dict(scores=scores, advantages=advantages.cpu(), steps=(~prob_masks).sum(1).float().mean().item(), logs=logs)

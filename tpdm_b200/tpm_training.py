@@ -54,7 +54,11 @@ class TimePredictorTrainer:
         self.off = list(off)
         n = self.off[12]
         self.params = torch.zeros(n, device=dev, dtype=torch.float32)
-        self.grads = torch.zeros_like(self.params)
+        # ONE buffer goes through the data-parallel all-reduce: the gradients followed by {loss, non-finite-loss flag}
+        # (rloo_trainer.py:497-501: gather(loss) + NaN guard + backward become one exchange; SURVEY 2.3 C3 + C4)
+        self.reduce_buf = torch.zeros(n + 2, device=dev, dtype=torch.float32)
+        self.grads = self.reduce_buf[:n]
+        self.tail = self.reduce_buf[n:]
         self.m, self.v = torch.zeros_like(self.params), torch.zeros_like(self.params)
         self.sumsq = torch.zeros(1, device=dev, dtype=torch.float64)
         self.n_conv1 = sd["conv1.weight"].numel()
@@ -110,6 +114,7 @@ class TimePredictorTrainer:
         if x.shape != (ns, self.g, self.g, 2 * self.D) or t.shape != (ns, self.D):
             raise ValueError(f"expected x (ns,{self.g},{self.g},{2 * self.D}) and temb (ns,{self.D}); got {tuple(x.shape)}, {tuple(t.shape)}")
         self._keep = (x, t)   # borrowed by the library until backward() has run
+        self._generation = getattr(self, "_generation", 0) + 1   # the saved activations belong to THIS forward
         ab = torch.empty(ns, 2, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             L.check(lib.tpdm_tpm_train_forward(self.handle, L.ptr(x), L.ptr(t), ns, L.ptr(ab), L.stream_ptr()))
@@ -124,8 +129,12 @@ class TimePredictorTrainer:
     # ---- one micro-batch of rloo_trainer.py:485-523 ------------------------------------------------------------------
     def ppo_update(self, sigmas: torch.Tensor, old_logprobs: torch.Tensor, tpm_inputs_nhwc: torch.Tensor, tembs: torch.Tensor,
                    advantages: torch.Tensor, min_sigma: float, cliprange: float = 0.2, epsilon: float = 1e-3, relative: bool = True,
-                   optimizer_step: bool = True) -> Dict[str, torch.Tensor]:
-        """sigmas / old_logprobs (mb, T); tpm_inputs_nhwc (mb, T, g, g, 2D) bf16; tembs (mb, T, D); advantages (mb,)."""
+                   optimizer_step: bool = True, prediction_type: str = "alpha_beta", all_reduce: bool = True) -> Dict[str, torch.Tensor]:
+        """sigmas / old_logprobs (mb, T); tpm_inputs_nhwc (mb, T, g, g, 2D) bf16; tembs (mb, T, D); advantages (mb,).
+        Returns device scalars: loss (mean over ranks), clipfrac, approxkl, ratio, nonfinite (how many ranks saw a NaN / Inf
+        loss: > 0 means the optimizer step was skipped on EVERY rank) and, with optimizer_step, grad_norm."""
+        if prediction_type not in ("alpha_beta", "mode_concentration"):
+            raise ValueError(f"unknown prediction_type {prediction_type!r}")
         lib = L.load()
         mb, T = sigmas.shape
         f32 = dict(device=self.device, dtype=torch.float32)
@@ -136,23 +145,76 @@ class TimePredictorTrainer:
         stats = torch.empty(4, **f32)
         with torch.cuda.device(self.device):
             L.check(lib.tpdm_ppo_clip_loss(L.ptr(ab), L.ptr(sig), L.ptr(old), L.ptr(adv), mb, T, float(min_sigma), float(epsilon),
-                                           1 if relative else 0, float(cliprange), float(self.module.epsilon), L.ptr(new_lp), L.ptr(dz),
-                                           L.ptr(stats), L.stream_ptr()))
-        self.backward(dz)
+                                           1 if relative else 0, 0 if prediction_type == "alpha_beta" else 1, float(cliprange),
+                                           float(self.module.epsilon), L.ptr(new_lp), L.ptr(dz), L.ptr(stats), self.tail.data_ptr(),
+                                           L.stream_ptr()))
+        self.backward(dz)      # overwrites self.grads; the tail written above sits right behind them
         world = dist.get_world_size() if dist.is_initialized() else 1
-        if world > 1:   # the only exchange step of the path: TPM gradients, one flat buffer (rloo_trainer.py:501 under DDP / ZeRO-0)
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
-        out = dict(loss=stats[0], clipfrac=stats[1], approxkl=stats[2], ratio=stats[3], new_logprobs=new_lp)
+        if not all_reduce:      # local gradient only (tests of the exchange itself)
+            world = 1
+        if world > 1:   # the only exchange step of the path: TPM gradients + loss + NaN flag in ONE buffer (rloo_trainer.py:497-501)
+            dist.all_reduce(self.reduce_buf, op=dist.ReduceOp.SUM)
+        out = dict(loss=self.tail[0] / world, local_loss=stats[0], clipfrac=stats[1], approxkl=stats[2], ratio=stats[3],
+                   nonfinite=self.tail[1].clone(), new_logprobs=new_lp)
         if optimizer_step:
-            out["grad_norm"] = self.optimizer_step(grad_scale=1.0 / world)
+            out["grad_norm"] = self.optimizer_step(grad_scale=1.0 / world, guard=True)
         return out
 
-    def optimizer_step(self, grad_scale: float = 1.0) -> torch.Tensor:
+    def optimizer_step(self, grad_scale: float = 1.0, guard: bool = False) -> torch.Tensor:
+        """Fused global-norm clip + AdamW on the flat buffers.  ``guard``: skip the update (on the device, no host sync) when
+        the all-reduced non-finite-loss flag of the last ppo_update is set."""
         lib = L.load()
         self.step_count += 1
         with torch.cuda.device(self.device):
             L.check(lib.tpdm_adamw_step(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.m), L.ptr(self.v), self.params.numel(), float(self.lr),
                                         float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.weight_decay),
                                         float(self.max_grad_norm), self.step_count, float(grad_scale), L.ptr(self.sumsq),
-                                        L.ptr(self.conv1_bf16), self.n_conv1, L.stream_ptr()))
+                                        L.ptr(self.conv1_bf16), self.n_conv1, self.tail.data_ptr() + 4 if guard else None, L.stream_ptr()))
         return self.sumsq.sqrt().float()
+
+    # ---- autograd hook for the reference trainer's own loop ----------------------------------------------------------
+    def logprobs(self, sigmas: torch.Tensor, tpm_inputs_nhwc: torch.Tensor, tembs: torch.Tensor, min_sigma: float, epsilon: float = 1e-3,
+                 relative: bool = True, prediction_type: str = "alpha_beta") -> torch.Tensor:
+        """only_predict_logprobs (modeling_sd3_pnt.py:670-726) as a differentiable function of the module's parameters:
+        (mb, T) log-probs whose ``.backward()`` deposits into ``time_predictor.<name>.grad`` in PyTorch layouts, so that
+        ``accelerator.backward(loss)`` / DDP all-reduce / ``clip_grad_norm_`` / ``optimizer.step`` of the reference trainer
+        (rloo_trainer.py:485-523) run unmodified.  Forward and backward are the native kernels."""
+        params = [p for _, p in self.module.named_parameters()]
+        names = [n for n, _ in self.module.named_parameters()]
+        self.load_from_module()      # an external optimizer may have stepped the module since the last call
+        return _LogprobReplay.apply(self, names, sigmas, tpm_inputs_nhwc, tembs, float(min_sigma), float(epsilon), bool(relative),
+                                    prediction_type, *params)
+
+
+class _LogprobReplay(torch.autograd.Function):
+    """forward: tpdm_tpm_train_forward + tpdm_beta_logprob; backward: dz = dlogprob/dz * grad -> tpdm_tpm_train_backward."""
+
+    @staticmethod
+    def forward(ctx, trainer, names, sigmas, x_nhwc, tembs, min_sigma, epsilon, relative, prediction_type, *params):
+        lib = L.load()
+        mb, T = sigmas.shape
+        f32 = dict(device=trainer.device, dtype=torch.float32)
+        ab = trainer.forward(x_nhwc.reshape(mb * T, trainer.g, trainer.g, 2 * trainer.D), tembs.reshape(mb * T, trainer.D))
+        sig = sigmas.to(**f32).contiguous()
+        lp = torch.empty(mb, T, **f32)
+        dlp = torch.empty(mb * T, 2, **f32)
+        with torch.cuda.device(trainer.device):
+            L.check(lib.tpdm_beta_logprob(L.ptr(ab), L.ptr(sig), mb, T, min_sigma, epsilon, 1 if relative else 0,
+                                          0 if prediction_type == "alpha_beta" else 1, float(trainer.module.epsilon), L.ptr(lp), L.ptr(dlp),
+                                          L.stream_ptr()))
+        ctx.trainer, ctx.names, ctx.dlp, ctx.shape, ctx.generation = trainer, names, dlp, (mb, T), trainer._generation
+        ctx.param_meta = [(p.shape, p.dtype) for p in params]
+        return lp
+
+    @staticmethod
+    def backward(ctx, grad_lp):
+        trainer = ctx.trainer
+        mb, T = ctx.shape
+        if trainer._generation != ctx.generation:
+            raise RuntimeError("TimePredictor replay: backward() after a later forward() -- the saved activations were overwritten "
+                               "(call backward on each micro-batch before replaying the next, as rloo_trainer.py:485-501 does)")
+        dz = ctx.dlp * grad_lp.to(device=trainer.device, dtype=torch.float32).reshape(mb * T, 1)
+        trainer.backward(dz)
+        grads = trainer.tensors(trainer.grads)
+        out = [grads[n].to(dt).contiguous() for n, (shape, dt) in zip(ctx.names, ctx.param_meta)]
+        return (None,) * 9 + tuple(out)

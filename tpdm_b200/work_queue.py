@@ -14,9 +14,17 @@ import torch.distributed as dist
 
 
 class PromptQueue:
+    """Contract: every rank constructs its PromptQueue objects of a given ``name`` in the same order (as with any collective).
+    The n-th queue of that name counts under its own store key ``<name>/<n>``, so a second ``sample_prompts`` call in the same
+    process group starts from zero again instead of inheriting the drained counter of the first."""
+
+    _epochs: Dict[str, int] = {}
+
     def __init__(self, n_prompts: int, name: str = "tpdm_prompt_ticket", store=None):
         self.n = int(n_prompts)
-        self.key = name
+        epoch = PromptQueue._epochs.get(name, 0)
+        PromptQueue._epochs[name] = epoch + 1
+        self.key = f"{name}/{epoch}"
         self._local = 0
         self.store = store
         if store is None and dist.is_available() and dist.is_initialized():

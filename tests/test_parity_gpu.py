@@ -85,20 +85,45 @@ def test_joint_attention(L, Bt, S, H, d, q_rows):
         assert float(out[..., d:].float().abs().max()) == 0.0
 
 
-def test_attention_large_logits_trigger_rescale(L):
-    """Rows whose running max grows by more than 2^8 between KV tiles exercise the lazy O-rescale path."""
+@pytest.mark.parametrize("jump", [10, 40, 70, 100, 300, 330, 370, 511, "ramp"])
+def test_attention_large_logits_trigger_rescale(L, jump):
+    """Rows whose running max grows by far more than 2^32 between keys exercise the lazy reference update: the jump is placed
+    in every 32-key chunk position of a 128-key tile (chunks 0/1 are rescaled before their P is handed to the MMA warp, chunks
+    2/3 after the first half of P V has been issued), in the first and in later tiles, and as a ramp that moves it many times."""
     torch.manual_seed(2)
     lib = L.load()
     Bt, S, H, d = 1, 512, 2, 64
     qkv = torch.randn(Bt, S, 3, H, d, device="cuda")
     qkv[:, :, 0] *= 6.0
-    qkv[:, 300:, 1] *= 6.0     # later key tiles carry much larger logits
+    if jump == "ramp":
+        qkv[:, :, 1] *= torch.linspace(0.5, 12.0, S, device="cuda").view(1, S, 1, 1)
+    else:
+        qkv[:, jump:, 1] *= 6.0     # later keys carry much larger logits
     qkv = qkv.bfloat16().contiguous()
     out = torch.zeros(Bt, S, H, d, device="cuda", dtype=torch.bfloat16)
     q, k, v = (qkv[:, :, i].float().transpose(1, 2) for i in range(3))
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2)
     L.check(lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, 64, d, 0, None))
     torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 1e-2
+
+
+def test_attention_extreme_logits_stay_finite(L):
+    """Scores of +-1e4 (far beyond exp range in fp32 without a reference): softmax degenerates to a one-hot pick of the arg-max key."""
+    torch.manual_seed(9)
+    lib = L.load()
+    Bt, S, H, d = 1, 384, 1, 64
+    qkv = torch.randn(Bt, S, 3, H, d, device="cuda")
+    qkv[:, :, 0] *= 40.0
+    qkv[:, :, 1] *= 40.0
+    qkv = qkv.bfloat16().contiguous()
+    out = torch.zeros(Bt, S, H, d, device="cuda", dtype=torch.bfloat16)
+    q, k, v = (qkv[:, :, i].float().transpose(1, 2) for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2)
+    L.check(lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, 64, d, 0, None))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
     assert rel(out, ref) < 1e-2
 
 

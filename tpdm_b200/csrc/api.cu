@@ -501,13 +501,8 @@ int tpdm_sample_begin(tpdm_plan* p, const float* latents, const float* neg_embed
   TPDM_CUDA_OK(cudaMemcpyAsync(p->latents, latents, lat * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if (ratios)
     TPDM_CUDA_OK(cudaMemcpyAsync(p->ratios, ratios, static_cast<size_t>(p->B) * p->max_steps * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  // sigma = ones (modeling_sd3_pnt.py:508)
-  std::vector<float> ones(static_cast<size_t>(p->B) * (p->max_steps + 1), 0.f);
-  for (int b = 0; b < p->B; ++b) ones[static_cast<size_t>(b) * (p->max_steps + 1)] = 1.0f;
-  TPDM_CUDA_OK(cudaMemcpyAsync(p->sigma_hist, ones.data(), ones.size() * sizeof(float), cudaMemcpyHostToDevice, s));
-  TPDM_CUDA_OK(cudaStreamSynchronize(s));  // `ones` is pageable host memory going out of scope
-  TPDM_CUDA_OK(cudaMemsetAsync(p->all_done, 0, sizeof(int) * p->max_steps, s));
-  TPDM_CUDA_OK(cudaMemsetAsync(p->masks, 0, sizeof(int) * p->B * p->max_steps, s));
+  // sigma = ones (modeling_sd3_pnt.py:508); stream-ordered like everything else (no host staging, no synchronisation)
+  TPDM_TRY(k_sample_init(p->sigma_hist, p->masks, p->all_done, p->B, p->max_steps, s));
   TPDM_TRY(set_prompts(p, neg_embeds, pos_embeds, neg_pooled, pos_pooled, s));
   p->begun = 1;
   return 0;

@@ -8,30 +8,31 @@
 //
 // One CTA = one 128-row query tile of one (batch, head); 256 threads; two CTAs co-resident per SM (dp = 64).
 //   warp 0      TMA producer  (Q once, K/V tiles of 128 keys through a 2-stage smem ring)
-//   warp 1      MMA issuer for S.  Keys are consumed in HALF-tiles of 64:  S[b] = Q K_half^T (SS, 128x64xdp), b = parity
-//   warp 3      MMA issuer for O += P[b] V_half (A = P from TMEM, B = V MN-major from smem)
+//   warp 1      MMA issuer for S = Q K^T: one 128 x 128 score tile per K tile (SS, dp/16 instructions of N = 128)
+//   warp 3      MMA issuer for O += P V (A = P from TMEM, B = V MN-major from smem, 8 instructions of N = dp)
 //   warp 2      TMEM allocator
 //   warps 4-7   softmax, one thread per query row.
-// S and P are DOUBLE-BUFFERED in TMEM (S[2] 64 fp32 columns each, P[2] 32 packed-bf16 columns each, O dp columns), so the
-// softmax warps never wait for the tensor core in steady state: while they work on half-tile i the MMA warps have already
-// produced S(i+1) and are accumulating P(i-1) V.
-// Softmax: fp32, exp2 with log2(e)/sqrt(d) folded into one FFMA2, ONE pass per half-tile against a reference max that is
-// fixed by the first half-tile and not tracked afterwards: fp32 sums and bf16 P carry 8 exponent bits, so the result stays
-// exact (the final 1/l cancels the reference) until a row grows past 2^128 relative to it.  That is detected from the row
-// sum before P is published; such a half-tile, the first one and the masked tail take an exact two-pass route that moves
-// the reference and rescales O and l once the outstanding P V has drained.
+// TMEM per CTA: S 128 fp32 columns, P 64 columns (128 keys of packed bf16), O dp columns -- ONE buffer each.  Overlap inside a
+// CTA comes from releasing S as soon as its last 32-column chunk is in registers (Q K^T of the next tile then runs under the
+// last quarter of this tile's exponentials and under P V), overlap on the SM from the second co-resident CTA.
 //
-// Where the time goes (ncu source-level samples, profiles/r01_attention_ncu.txt): per 64-key half-tile and CTA the kernel
-// needs 512 cycles of the MUFU pipe (ex2, 16 / clk / SM) AND 512 cycles of the TMEM read port (S in fp32, 64 B / clk / SM)
-// -- both floors are 214 us for S = 4429, H = 24, Bt = 2 -- against 256 cycles of tensor pipe; it runs at 61 % of either.
-// Measured and rejected: tracking the half-tile's own max (32 FMNMX3 per row and half-tile; removing it changed nothing,
-// so it was dropped), 8 softmax warps with the columns of a half-tile split between two warps per lane quarter (360 us
-// stand-alone, 3 % slower in the trajectory), prefetching the next half-tile's first 32 S columns during the second
-// exponential block (398 us: 128 registers and spills), a second MMA-issuing warp for P V (kept, +2 %).  With the
-// exponentials compiled out the kernel still takes 260 us, so MUFU and the TMEM-read side are about equally loaded.
-// Not tried: fp16 accumulators for S (half the TMEM read) -- the error it adds grows with the logit magnitude and cannot
-// be checked against real checkpoints offline (random-init weights give near-uniform attention).
+// Why 128-key tiles (round 2; measurements in profiles/r02_*.txt):
+//  * tools/microbench/mma_issue_rate.cu: one thread cannot issue tcgen05.mma faster than one per ~56 cycles, whatever its size,
+//    and four issuers on one SM get 90-140 cycles each.  The round-1 kernel issued N = 64 MMAs (32 tensor cycles each) and its
+//    timeline (tools/attn_trace.py) showed 539 cycles per 64 keys in the Q K^T issuer alone; N = 128 halves the instruction count.
+//  * the same timeline showed ~625 of the 1460 cycles a softmax warp spent per 64 keys in mbarrier round trips, exposed TMEM
+//    load latency and the P hand-over; with 128 keys per round trip that cost is halved, and the chunk loads are software
+//    pipelined (the load of chunk c+1 is in flight while chunk c is exponentiated).
+//  * tools/microbench/tmem_read_rate.cu: tcgen05.ld moves 490-1050 B/clk/SM, so reading S back in fp32 is NOT a floor (round 1
+//    assumed 64 B/clk/SM); the floor of this kernel is the MUFU: 16 ex2 / clk / SM = 1024 cycles per 128 x 128 scores.
+// Softmax: fp32, exp2 with log2(e)/sqrt(d) folded into one FFMA2, against a reference maximum m_used that is raised lazily: every
+// 32-column chunk computes its own maximum (FMNMX3 trees, issued under the MUFU work of the previous chunk) and only when that
+// exceeds m_used by more than 2^kRescaleThreshold does the row take the (rare, exact) path that moves the reference and rescales
+// what was accumulated under the old one -- O, l and the P chunks of this tile already stored.  fp32 sums and bf16 P carry 8 exponent bits, so running up
+// to 2^32 above the reference costs no precision, and the final 1/l cancels the reference.
 #include <cuda_bf16.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "host.h"
@@ -42,22 +43,21 @@ namespace {
 
 constexpr int kAttnThreads = 256;
 constexpr int kQT = 128;   // query rows per CTA
-constexpr int kKT = 128;   // keys per K/V smem tile
-constexpr int kHT = 64;    // keys per half-tile (one S / P buffer)
+constexpr int kKT = 128;   // keys per K/V smem tile = keys per S tile
+constexpr int kChunk = 32; // S columns per tcgen05.ld
 constexpr int kKVStages = 2;
-constexpr float kRescaleThreshold = 8.0f;  // log2 units
-// Every kPolyEvery-th pair of exponentials on the fast path is computed on the FMA/ALU pipes (Cody-Waite range
-// reduction + cubic minimax polynomial, max relative error 7.5e-5 -- P is rounded to bf16 anyway) instead of MUFU.EX2,
-// meant to relieve the 16/clk/SM MUFU rate.  MEASURED on B200 (S=4429, H=24, Bt=2): 0 -> 359 us, 1/8 -> 376 us,
-// 1/4 -> 400 us, 1/2 -> 418 us: the softmax warps are issue/latency bound, so the extra instructions cost more than the
-// MUFU slots they free.  Left in for head dims / occupancies where MUFU does bind; 0 disables the emulation.
+constexpr float kRescaleThreshold = 32.0f;  // log2 units
+// Every kPolyEvery-th pair of exponentials is computed on the FMA/ALU pipes (Cody-Waite range reduction + cubic minimax
+// polynomial, max relative error 7.5e-5 -- P is rounded to bf16 anyway) instead of MUFU.EX2; 0 disables the emulation.
+// Measured on B200 with this kernel (S = 4429, H = 24, Bt = 2; profiles/r02_attention_experiments.txt): 0 -> 343 us, every 8th ->
+// 328 us, every 4th -> 324 us, every 2nd -> 325 us.  (Round 1's 64-key kernel was latency bound and got SLOWER with it.)
+// Packing P with integer adds + PRMT instead of F2FP (which shares the XU pipe with MUFU) was measured too: 358 us, rejected.
 #ifndef TPDM_POLY_EVERY
-#define TPDM_POLY_EVERY 0
+#define TPDM_POLY_EVERY 4
 #endif
 constexpr int kPolyEvery = TPDM_POLY_EVERY;
-
-// -DTPDM_ATTN_TRACE: clock64() time stamps of one CTA's softmax warp 4 (role 0, 8 slots per half-tile) and of the two MMA-issuing
-// warps (roles 1 and 2, 4 slots per half-tile), read back with tpdm_attn_trace_read (tools/attn_trace.py).  Diagnostic builds only.
+// -DTPDM_ATTN_TRACE: clock64() time stamps of one CTA's softmax warp 4 (role 0, 8 slots per key tile) and of the two MMA-issuing
+// warps (roles 1 and 2, 4 slots per key tile), read back with tpdm_attn_trace_read (tools/attn_trace.py).  Diagnostic builds only.
 #ifdef TPDM_ATTN_TRACE
 __device__ long long g_attn_trace[3][2048];
 #define ATRACE(role, idx)                                                                       \
@@ -77,8 +77,8 @@ struct AttnSmem {
   static constexpr int kBarOff = kVOff + kKVStages * kTile;
   static constexpr int kTotal = kBarOff + 256 + 1024;
   static constexpr uint32_t kTmemCols = DP == 64 ? 256 : 512;
-  static constexpr uint32_t kSCol = 0;     // S[b] at kSCol + 64 b
-  static constexpr uint32_t kPCol = 128;   // P[b] at kPCol + 32 b
+  static constexpr uint32_t kSCol = 0;     // S: 128 fp32 columns
+  static constexpr uint32_t kPCol = 128;   // P: 64 columns (128 keys, packed bf16)
   static constexpr uint32_t kOCol = 192;   // O: DP columns
 };
 
@@ -94,18 +94,17 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   uint64_t* v_full = k_full + kKVStages;       // [kKVStages]
   uint64_t* k_empty = v_full + kKVStages;      // [kKVStages]
   uint64_t* v_empty = k_empty + kKVStages;     // [kKVStages]
-  uint64_t* s_full = v_empty + kKVStages;      // [2]  MMA -> softmax : S[b] written
-  uint64_t* s_free = s_full + 2;               // [2]  softmax -> MMA : S[b] read into registers
-  uint64_t* p_full = s_free + 2;               // [2]  softmax -> MMA : P[b] written (and O rescaled if needed)
-  uint64_t* pv_done = p_full + 2;              // [2]  MMA -> softmax : P[b] V accumulated (P[b] may be overwritten)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* s_full = v_empty + kKVStages;      // MMA -> softmax : S(j) written
+  uint64_t* s_free = s_full + 1;               // softmax -> MMA : S(j) is in registers
+  uint64_t* p_full = s_free + 1;               // [2] softmax -> MMA : keys [0,64) / [64,128) of P(j) written (and O rescaled if needed)
+  uint64_t* pv_done = p_full + 2;              // MMA -> softmax : P(j) V accumulated (P may be overwritten, O may be touched)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int q0 = qt * kQT;
   const int n_kv = (A.S + kKT - 1) / kKT;
-  const int n_half = (A.S + kHT - 1) / kHT;
 #ifdef TPDM_ATTN_TRACE
   const bool trace_on = blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 0;
 #endif
@@ -123,12 +122,11 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       mbar_init(&k_empty[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&pv_done[i], 1);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, 4);
+    mbar_init(&p_full[0], 4);
+    mbar_init(&p_full[1], 4);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
   pdl_wait();
@@ -143,6 +141,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -168,106 +167,92 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
         }
       }
     }
-  } else if (warp == 1 || warp == 3) {
-    // ---------------------------------------------------------------- MMA issuers (warp 1: S = Q K^T, warp 3: O += P V)
-    constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kHT, false);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(kQT, DP, true);
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer: S(j) = Q K(j)^T
+    constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, false);
     const uint32_t q_base = smem_u32(smem + L::kQOff);
-
-    // half-tile i lives in K/V smem tile t = i/2 (ring stage t % 2, ring phase (t/2) & 1), rows [64 (i&1), +64)
-    auto issue_qk = [&](int i) {
-      const int t = i >> 1, hf = i & 1, stage = t % kKVStages;
-      ATRACE(1, 4 * i);
-      if (hf == 0) mbar_wait(&k_full[stage], (t / kKVStages) & 1);
-      if (i >= 2) mbar_wait(&s_free[i & 1], ((i - 2) >> 1) & 1);  // softmax(i-2) has read S[i&1]
+    mbar_wait(q_full, 0);
+    for (int j = 0; j < n_kv; ++j) {
+      const int stage = j % kKVStages;
+      ATRACE(1, 4 * j);
+      mbar_wait(&k_full[stage], (j / kKVStages) & 1);
+      if (j >= 1) mbar_wait(s_free, (j - 1) & 1);  // softmax(j-1) holds S(j-1) in registers
       tc_fence_after();
-      ATRACE(1, 4 * i + 1);
+      ATRACE(1, 4 * j + 1);
       if (lane == 0) {
-        const uint32_t k_base = smem_u32(smem + L::kKOff + stage * L::kTile) + hf * (kHT * 128);
-        const uint32_t s_tmem = tmem_base + L::kSCol + (i & 1) * kHT;
+        const uint32_t k_base = smem_u32(smem + L::kKOff + stage * L::kTile);
 #pragma unroll
         for (int ks = 0; ks < DP / 16; ++ks) {
           const uint32_t off = (ks / 4) * (kQT * 128) + (ks % 4) * 32;
-          umma_ss(s_tmem, make_smem_desc_sw128(q_base + off, 16, 1024), make_smem_desc_sw128(k_base + off, 16, 1024), idesc_qk,
-                  ks != 0 ? 1u : 0u);
+          umma_ss(tmem_base + L::kSCol, make_smem_desc_sw128(q_base + off, 16, 1024), make_smem_desc_sw128(k_base + off, 16, 1024),
+                  idesc_qk, ks != 0 ? 1u : 0u);
         }
-        umma_commit(&s_full[i & 1]);
-        if (hf == 1 || i == n_half - 1) umma_commit(&k_empty[stage]);
+        // ONE commit per tile: tcgen05.commit costs the issuing thread about as much as three MMAs (mma_issue_rate.cu); the K stage
+        // is handed back to the TMA warp by the softmax warp that observes s_full
+        umma_commit(s_full);
       }
-      ATRACE(1, 4 * i + 2);
+      ATRACE(1, 4 * j + 2);
       __syncwarp();
-    };
-    auto issue_pv = [&](int i) {
-      const int t = i >> 1, hf = i & 1, stage = t % kKVStages;
-      ATRACE(2, 4 * i);
-      mbar_wait(&p_full[i & 1], (i >> 1) & 1);
-      if (hf == 0) mbar_wait(&v_full[stage], (t / kKVStages) & 1);
-      tc_fence_after();
-      ATRACE(2, 4 * i + 1);
-      if (lane == 0) {
-        const uint32_t v_base = smem_u32(smem + L::kVOff + stage * L::kTile) + hf * (kHT * 128);
-        const uint32_t p_tmem = tmem_base + L::kPCol + (i & 1) * (kHT / 2);
-        const uint32_t o_tmem = tmem_base + L::kOCol;
-#pragma unroll
-        for (int ks = 0; ks < kHT / 16; ++ks) {
-          // B = V half-tile, MN-major: 16 keys per MMA = 16 rows of 128 B; 64-wide d-groups are kKT*128 B apart (LBO)
-          umma_ts(o_tmem, p_tmem + ks * 8, make_smem_desc_sw128(v_base + ks * 2048, kKT * 128, 1024), idesc_pv,
-                  (i | ks) != 0 ? 1u : 0u);
-        }
-        umma_commit(&pv_done[i & 1]);
-        if (hf == 1 || i == n_half - 1) umma_commit(&v_empty[stage]);
-      }
-      ATRACE(2, 4 * i + 2);
-      __syncwarp();
-    };
-
-    // QK and PV are issued by TWO warps.  Every tcgen05.mma costs the issuing thread ~150 cycles before the next one can
-    // go out, however small it is, and with one issuer the 16 MMAs per 128 keys (8 QK + 8 PV) -- not the softmax -- paced
-    // this kernel (every measured variant fits that model, see the list at the top).  All hand-offs between the two
-    // streams go through mbarriers (s_free / p_full / pv_done), none relies on a common issue order.
-    if (warp == 1) {
-      mbar_wait(q_full, 0);
-      for (int i = 0; i < n_half; ++i) issue_qk(i);
-    } else {
-      for (int i = 0; i < n_half; ++i) issue_pv(i);
     }
-  } else if (warp >= 4) {
+  } else if (warp == 3) {
+    // ---------------------------------------------------------------- MMA issuer: O += P(j) V(j)
+    // Two issuing warps: every tcgen05.mma costs its issuing thread >= 56 cycles (mma_issue_rate.cu); all hand-offs between
+    // the two instruction streams go through mbarriers (s_free / p_full / pv_done), none relies on a common issue order.
+    constexpr uint32_t idesc_pv = make_idesc_bf16(kQT, DP, true);
+    for (int j = 0; j < n_kv; ++j) {
+      const int stage = j % kKVStages;
+      ATRACE(2, 4 * j);
+      // P(j) arrives in two halves of 64 keys: the first four MMAs run under the last quarter of the tile's exponentials, so only
+      // four are left when the tile ends and P (single-buffered) is free again before the next tile's first chunk lands
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        mbar_wait(&p_full[half], j & 1);
+        if (half == 0) mbar_wait(&v_full[stage], (j / kKVStages) & 1);
+        tc_fence_after();
+        if (half == 0) ATRACE(2, 4 * j + 1);
+        if (lane == 0) {
+          const uint32_t v_base = smem_u32(smem + L::kVOff + stage * L::kTile);
+#pragma unroll
+          for (int k4 = 0; k4 < kKT / 32; ++k4) {
+            const int ks = half * (kKT / 32) + k4;
+            // B = V tile, MN-major: 16 keys per MMA = 16 rows of 128 B; 64-wide d-groups are kKT*128 B apart (LBO)
+            umma_ts(tmem_base + L::kOCol, tmem_base + L::kPCol + ks * 8, make_smem_desc_sw128(v_base + ks * 2048, kKT * 128, 1024), idesc_pv,
+                    (j | ks) != 0 ? 1u : 0u);
+          }
+          if (half == 1) umma_commit(pv_done);   // the V stage is released by the softmax warp that observes pv_done
+        }
+        __syncwarp();
+      }
+      ATRACE(2, 4 * j + 2);
+      __syncwarp();
+    }
+  }
+  } else {
     // ---------------------------------------------------------------- softmax / correction / epilogue
     const int q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_off + L::kSCol;
+    const uint32_t p_tmem = tmem_base + lane_off + L::kPCol;
     const uint32_t o_tmem = tmem_base + lane_off + L::kOCol;
     const float scale = A.scale_log2;
     const uint64_t scale2 = pack_f32x2(scale, scale);
-    float m_used = -INFINITY;            // reference max of the running sums (log2 domain); may lag the true max
+    float m_used = -INFINITY;            // reference max of the running sums (log2 domain); may lag the true max by 2^kRescaleThreshold
     uint64_t l2 = pack_f32x2(0.f, 0.f);  // row sum as two partial sums
-    float alpha_pending = 1.f;           // rescale discovered in half-tile i-1, applied before P(i) is published
-    bool need_pending = false;
 
-    auto rescale_o = [&](float alpha) {
-#pragma unroll
-      for (int c = 0; c < DP / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld_32x32(o_tmem + c * 32, o);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x32(o_tmem + c * 32, o);
-      }
-      l2 = fmul2(l2, pack_f32x2(alpha, alpha));
-    };
-    // p = exp2(s * scale - m) for one 32-column chunk, packed to bf16 into P; accumulates the row sum
-    auto exp_chunk = [&](const uint32_t (&v)[32], uint32_t p_dst, uint64_t negm2, const bool emulate) {
-      uint32_t pk[16];
+    // p = exp2(s * scale - m_used) for one half (16 columns) of a 32-column chunk, packed to bf16; accumulates the row sum
+    auto exp_half = [&](const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t negm2, const int half) {
       const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f), nmagic2 = pack_f32x2(-12582912.f, -12582912.f);
       const uint64_t mone2 = pack_f32x2(-1.f, -1.f);
       const uint64_t c0 = pack_f32x2(0.9999280572f, 0.9999280572f), c1 = pack_f32x2(0.6932609677f, 0.6932609677f),
                      c2 = pack_f32x2(0.2426111251f, 0.2426111251f), c3 = pack_f32x2(0.0551716499f, 0.0551716499f);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int ii = 0; ii < 8; ++ii) {
+        const int i = half * 8 + ii;
         float x0, x1, p0, p1;
         unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), scale2, negm2), x0, x1);
-        if (kPolyEvery > 0 && emulate && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
-          // 2^x = 2^n * 2^f, n = rint(x) read from the mantissa of x + 1.5*2^23, f = x - n in [-0.5, 0.5]
+        if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
+          // 2^x = 2^n * 2^f, n = rint(x) read from the mantissa of x + 1.5*2^23, f = x - n in [-0.5, 0.5].  x <= kRescaleThreshold
+          // by construction of m_used (no wrap of the exponent on the high side); below -126 the clamp flushes the result to ~0.
           const uint64_t xp = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
           const uint64_t t = fadd2(xp, magic2);
           const uint64_t fr = ffma2(fadd2(t, nmagic2), mone2, xp);
@@ -286,127 +271,150 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
         l2 = fadd2(l2, pack_f32x2(p0, p1));
         pk[i] = pack_bf16x2(p0, p1);
       }
-      tmem_st_32x16(p_dst, pk);
     };
-    auto chunk_max = [&](const uint32_t (&v)[32], float m) {
+    // rare path: multiply everything accumulated under the old reference by alpha = 2^(m_old - m_new)
+    auto rescale_o = [&](float alpha) {
+#pragma unroll 1
+      for (int c = 0; c < DP / 16; ++c) {
+        uint32_t o[16];
+        tmem_ld_32x16(o_tmem + c * 16, o);
+        tmem_wait_ld();
 #pragma unroll
-      for (int i = 0; i < 32; i += 2) m = fmax3(m, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-      return m;
+        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_32x16(o_tmem + c * 16, o);
+      }
+    };
+    auto rescale_p_chunk = [&](int c, float alpha) {
+      uint32_t pk[16];
+      tmem_ld_32x16(p_tmem + c * 16, pk);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float lo = __uint_as_float(pk[i] << 16) * alpha, hi = __uint_as_float(pk[i] & 0xffff0000u) * alpha;
+        pk[i] = pack_bf16x2(lo, hi);
+      }
+      tmem_st_32x16(p_tmem + c * 16, pk);
+    };
+    // keys >= S of the masked tail tile (warp-uniform branch) get s = -inf, i.e. p = 0
+    auto mask_chunk = [&](const int c, uint32_t (&v)[32], const int valid) {
+      if (valid < kKT) {
+#pragma unroll
+        for (int e = 0; e < kChunk; ++e)
+          if (c * kChunk + e >= valid) v[e] = 0xff800000u;
+      }
+    };
+    // scaled maximum of one chunk: four independent FMNMX3 chains
+    auto chunk_max = [&](const uint32_t (&v)[32]) {
+      float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[8]), m2 = __uint_as_float(v[16]), m3 = __uint_as_float(v[24]);
+#pragma unroll
+      for (int e = 1; e < 7; e += 2) {
+        m0 = fmax3(m0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        m1 = fmax3(m1, __uint_as_float(v[8 + e]), __uint_as_float(v[8 + e + 1]));
+        m2 = fmax3(m2, __uint_as_float(v[16 + e]), __uint_as_float(v[16 + e + 1]));
+        m3 = fmax3(m3, __uint_as_float(v[24 + e]), __uint_as_float(v[24 + e + 1]));
+      }
+      m0 = fmax3(m0, __uint_as_float(v[7]), m1);
+      m2 = fmax3(m2, __uint_as_float(v[15]), m3);
+      return fmax3(m0, fmax3(m2, __uint_as_float(v[23]), __uint_as_float(v[31])), m0) * scale;
     };
 
-    for (int i = 0; i < n_half; ++i) {
-      const int bb = i & 1;
-      const uint32_t s_tmem = tmem_base + lane_off + L::kSCol + bb * kHT;
-      const uint32_t p_tmem = tmem_base + lane_off + L::kPCol + bb * (kHT / 2);
-      const int valid = A.S - i * kHT;  // keys valid in this half-tile (>= 1)
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = A.S - j * kKT;  // keys valid in this tile (>= 1)
 #ifdef TPDM_ATTN_TRACE
       const bool tr4 = trace_on && warp == 4;
-#define STRACE(e) do { if (tr4 && lane == 0 && 8 * i + (e) < 2048) g_attn_trace[0][8 * i + (e)] = clock64(); } while (0)
+#define STRACE(e) do { if (tr4 && lane == 0 && 8 * j + (e) < 2048) g_attn_trace[0][8 * j + (e)] = clock64(); } while (0)
 #else
 #define STRACE(e)
 #endif
       STRACE(0);
-      mbar_wait(&s_full[bb], (i >> 1) & 1);
-      if (i >= 2) mbar_wait(&pv_done[bb], ((i - 2) >> 1) & 1);  // P(i-2) V done: P[bb] may be overwritten
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
+      if (warp == 4 && lane == 0) mbar_arrive(&k_empty[j % kKVStages]);   // Q K(j)^T has completed: the K stage is free
       STRACE(1);
-      if (__any_sync(0xffffffffu, need_pending)) {
-        // every P V issued so far must have drained before O is touched (P(i-1) V is the newest; the MMAs retire in order)
-        mbar_wait(&pv_done[bb ^ 1], ((i - 1) >> 1) & 1);
-        tc_fence_after();
-        rescale_o(alpha_pending);
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(s_tmem, va);
+      // rare path, entered by the whole warp when any row's chunk maximum runs more than 2^kRescaleThreshold above its reference
+      // (always for the very first chunk, m_used = -inf): move the reference, rescale O, l and the P chunks [0, c) of this tile.
+      // Nothing of this tile has been handed to the MMA warp yet (hand-over happens after the maximum of its last chunk is known).
+      auto raise_reference = [&](const int c, const float mc) {
+        const bool need = mc > m_used + kRescaleThreshold;
+        const float alpha = need ? exp2_approx(m_used - mc) : 1.f;   // 0 when nothing has been accumulated yet
+        if (need) m_used = mc;
+        if (j > 0) {
+          // O holds P V of every earlier tile: all of them must have drained (P(j-1) V is the newest issued) before O is touched
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          rescale_o(alpha);
+        }
+        if (c > 0) {
+          tmem_wait_st();   // the chunks of this tile stored so far
+#pragma unroll 1
+          for (int cc = 0; cc < c; ++cc) rescale_p_chunk(cc, alpha);
+        }
+        l2 = fmul2(l2, pack_f32x2(alpha, alpha));
+      };
+      // Software pipeline over the four chunks: on entry `cur` (chunk c) is in registers with its reference settled and the load
+      // of `nxt` (chunk c+1) is in flight.  The wait for nxt and its maximum sit between the two halves of cur's exponentials,
+      // i.e. in the shadow of the MUFU; the load of chunk c+2 is issued into cur's registers once they are dead.
+      // (Measured and rejected, profiles/r02_attention_experiments.txt: the whole S tile in 128 registers with setmaxnreg 56 / 200,
+      // S released at 10 % of the tile and P chunk 0 held in registers instead of waiting for P(j-1) V -- no wait on data left, yet
+      // 375 us against 339 us: every mbarrier / tcgen05.wait placed between the halves of a chunk drains the warp's MUFU queue.)
+      tmem_wait_ld();
+      STRACE(2);
+      tmem_ld_32x32(s_tmem + kChunk, vb);
+      mask_chunk(0, va, valid);
+      {
+        const float mc = chunk_max(va);
+        if (__any_sync(0xffffffffu, mc > m_used + kRescaleThreshold)) raise_reference(0, mc);
       }
-      need_pending = false;
-      alpha_pending = 1.f;
-      bool fast_ok = false;
-      if (i > 0 && valid >= kHT) {
-        // ---- fast path: one pass against the reference max m_used, which is NOT updated here.  fp32 sums and bf16 P carry an
-        // 8-bit exponent, so p = 2^(s - m_used) stays exact in relative terms however far the true row max has moved past
-        // m_used -- until 2^128.  Overflow is detected after the fact (an infinite row sum) BEFORE P is published; S[bb] is
-        // released only after that check, so the exact route below can redo the half-tile and move m_used.  This drops the
-        // 32 FMNMX3 and their dependent chain per half-tile that tracking the tile's own max cost.
-        const uint64_t l_save = l2;
+      auto do_chunk = [&](const int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
+        constexpr int kLast = kKT / kChunk - 1;
+        uint32_t pk[16];
         const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
-        uint32_t va[32], vb[32];
-        tmem_ld_32x32(s_tmem, va);
-        tmem_wait_ld();
-        STRACE(2);
-        tmem_ld_32x32(s_tmem + 32, vb);
-        exp_chunk(va, p_tmem, negm2, true);
-        STRACE(3);
-        tmem_wait_ld();
-        STRACE(4);
-        exp_chunk(vb, p_tmem + 16, negm2, true);
-        float l_lo, l_hi;
-        unpack_f32x2(l2, l_lo, l_hi);
-        const bool overflow = !(l_lo + l_hi < 1e37f);  // inf, NaN, or close enough to the bf16 / fp32 limit to round to inf
-        if (!__any_sync(0xffffffffu, overflow)) {
-          fast_ok = true;
-          STRACE(5);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[bb]);
-          STRACE(6);
-        } else {
-          l2 = l_save;  // S[bb] is still intact (s_free not signalled): redo on the exact route
-        }
-      }
-      if (!fast_ok) {
-        // ---- exact two-pass route: first half-tile, masked tail, or a jump of the row max above 2^100
-        float m_tile = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < kHT / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_tmem + c * 32, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            float sv = __uint_as_float(v[e]);
-            if (c * 32 + e >= valid) sv = -INFINITY;
-            m_tile = fmaxf(m_tile, sv);
-          }
-        }
-        m_tile *= scale;
-        if (i == 0) {
-          m_used = m_tile;
-        } else {
-          const bool need = m_tile > m_used + kRescaleThreshold;
-          const float alpha = need ? exp2_approx(m_used - m_tile) : 1.f;
-          if (need) m_used = m_tile;
-          if (__any_sync(0xffffffffu, need)) {
-            mbar_wait(&pv_done[bb ^ 1], ((i - 1) >> 1) & 1);
-            tc_fence_after();
-            rescale_o(alpha);
-          }
-        }
-        const uint64_t negm2 = pack_f32x2(-m_used, -m_used);
-#pragma unroll
-        for (int c = 0; c < kHT / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_tmem + c * 32, v);
-          tmem_wait_ld();
-          if (c == kHT / 32 - 1) {
+        exp_half(cur, pk, negm2, 0);
+        float mnext = -INFINITY;
+        if (c < kLast) {
+          tmem_wait_ld();   // chunk c+1
+          if (c + 1 == kLast) {
+            // all of S(j) is in registers: Q K^T of the next tile may overwrite it
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[bb]);
+            if (lane == 0) mbar_arrive(s_free);
           }
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (c * 32 + e >= valid) v[e] = 0xff800000u;  // -inf -> p = 0
-          exp_chunk(v, p_tmem + c * 16, negm2, false);
+          mask_chunk(c + 1, nxt, valid);
+          mnext = chunk_max(nxt);
         }
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[bb]);
-      STRACE(7);
+        exp_half(cur, pk, negm2, 1);
+        if (c == 0 && j > 0) {  // P is single-buffered: P(j-1) V must be done before P(j) lands
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          if (warp == 4 && lane == 0) mbar_arrive(&v_empty[(j - 1) % kKVStages]);   // ... and its V stage is free
+        }
+        tmem_st_32x16(p_tmem + c * 16, pk);
+        if (c + 2 <= kLast) tmem_ld_32x32(s_tmem + (c + 2) * kChunk, cur);
+        if (c < kLast && __any_sync(0xffffffffu, mnext > m_used + kRescaleThreshold)) raise_reference(c + 1, mnext);
+        // Hand-over to the MMA warp: keys [0,64) once the reference of the WHOLE tile is settled (the maximum of the last chunk is
+        // known after chunk 2, so a raise never has to touch P that is already being multiplied), keys [64,128) at the end
+        if (c >= kLast - 1) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[c == kLast ? 1 : 0]);
+        }
+        if (c == 0) STRACE(3);
+      };
+      do_chunk(0, va, vb);
+      do_chunk(1, vb, va);
+      do_chunk(2, va, vb);
+      STRACE(4);
+      do_chunk(3, vb, va);
+      STRACE(5);
     }
     float l_lo, l_hi;
     unpack_f32x2(l2, l_lo, l_hi);
     const float l = l_lo + l_hi;
     // epilogue: O / l -> bf16, token-major
-    mbar_wait(&pv_done[(n_half - 1) & 1], ((n_half - 1) >> 1) & 1);
+    mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const int row = q0 + q * 32 + lane;
     const float inv_l = 1.0f / l;

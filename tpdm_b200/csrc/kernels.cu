@@ -1185,6 +1185,21 @@ int k_queue_move(const int* slot_prompt, const int* slot_flush, const int* slot_
   return 0;
 }
 
+// sigma_hist[b][0] = 1 (modeling_sd3_pnt.py:508), the rest of the per-trajectory state zeroed: one launch, no host staging buffer
+__global__ void sample_init_kernel(float* __restrict__ sigma_hist, int* __restrict__ masks, int* __restrict__ all_done, int B, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B * (T + 1)) sigma_hist[i] = (i % (T + 1)) == 0 ? 1.0f : 0.0f;
+  if (i < B * T) masks[i] = 0;
+  if (i < T) all_done[i] = 0;
+}
+
+int k_sample_init(float* sigma_hist, int* masks, int* all_done, int B, int T, cudaStream_t s) {
+  sample_init_kernel<<<blocks_for(static_cast<long long>(B) * (T + 1), 256), 256, 0, s>>>(sigma_hist, masks, all_done, B, T);
+  count_launch();
+  TPDM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int k_schedule(const ScheduleArgs& a, cudaStream_t s) {
   TPDM_CHECK(a.B <= 1024, TPDM_ERR_SHAPE, "schedule: batch %d > 1024", a.B);
   const int threads = ((a.B + 31) / 32) * 32;

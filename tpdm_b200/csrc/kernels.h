@@ -78,6 +78,8 @@ struct ScheduleArgs {
 // y[i] = bias[i % C] + sum_s part[s * n + i]: adds up the partial products of a split-K GEMM (n % 4 == 0, C % 4 == 0)
 int k_sum_partials(const float* part, int splits, long long n, const float* bias, int C, float* y, cudaStream_t s);
 int k_schedule(const ScheduleArgs& a, cudaStream_t s);
+// start of a trajectory: sigma_hist[b] = (1, 0, ..., 0), masks = 0, all_done = 0
+int k_sample_init(float* sigma_hist, int* masks, int* all_done, int B, int T, cudaStream_t s);
 
 // ---- device-side prompt queue (continuous batching over a fixed number of in-flight slots) ---------------------------
 struct QueueArgs {

@@ -83,6 +83,7 @@ def build_variant(name: str, defines, sources=None) -> str:
 if __name__ == "__main__":
     if "--variant" in sys.argv:
         i = sys.argv.index("--variant")
-        print(build_variant(sys.argv[i + 1], sys.argv[i + 2].split(","), ["attention_tcgen05.cu"]))
+        only = sys.argv[i + 3].split(",") if len(sys.argv) > i + 3 else ["attention_tcgen05.cu"]
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2].split(","), only))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -151,12 +151,12 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(&k_empty[stage], phase ^ 1);
+        mbar_wait_backoff(&k_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&k_full[stage], L::kTile);
 #pragma unroll
         for (int hh = 0; hh < DP / 64; ++hh)
           tma_load_4d(smem + L::kKOff + stage * L::kTile + hh * (kKT * 128), &A.tmK, &k_full[stage], hh * 64, h, j * kKT, b);
-        mbar_wait(&v_empty[stage], phase ^ 1);
+        mbar_wait_backoff(&v_empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&v_full[stage], L::kTile);
 #pragma unroll
         for (int hh = 0; hh < DP / 64; ++hh)
@@ -176,20 +176,20 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       const int stage = j % kKVStages;
       ATRACE(1, 4 * j);
       mbar_wait(&k_full[stage], (j / kKVStages) & 1);
-      if (j >= 1) mbar_wait(s_free, (j - 1) & 1);  // softmax(j-1) holds S(j-1) in registers
+      if (j >= 1) mbar_wait_backoff(s_free, (j - 1) & 1);  // softmax(j-1) holds S(j-1) in registers
       tc_fence_after();
       ATRACE(1, 4 * j + 1);
-      if (lane == 0) {
+      {
+        // converged warp, one elected lane per instruction (umma_ss_elect in common.cuh): no waterfall loop around the MMAs
         const uint32_t k_base = smem_u32(smem + L::kKOff + stage * L::kTile);
+        const uint64_t qdesc0 = make_smem_desc_sw128(q_base, 16, 1024), kdesc0 = make_smem_desc_sw128(k_base, 16, 1024);
 #pragma unroll
         for (int ks = 0; ks < DP / 16; ++ks) {
-          const uint32_t off = (ks / 4) * (kQT * 128) + (ks % 4) * 32;
-          umma_ss(tmem_base + L::kSCol, make_smem_desc_sw128(q_base + off, 16, 1024), make_smem_desc_sw128(k_base + off, 16, 1024),
-                  idesc_qk, ks != 0 ? 1u : 0u);
+          const uint32_t off = ((ks / 4) * (kQT * 128) + (ks % 4) * 32) >> 4;   // the start-address field counts 16-byte units
+          umma_ss_elect(tmem_base + L::kSCol, qdesc0 + off, kdesc0 + off, idesc_qk, ks != 0 ? 1u : 0u);
         }
-        // ONE commit per tile: tcgen05.commit costs the issuing thread about as much as three MMAs (mma_issue_rate.cu); the K stage
-        // is handed back to the TMA warp by the softmax warp that observes s_full
-        umma_commit(s_full);
+        // ONE commit per tile: the K stage is handed back to the TMA warp by the softmax warp that observes s_full
+        umma_commit_elect(s_full);
       }
       ATRACE(1, 4 * j + 2);
       __syncwarp();
@@ -206,20 +206,20 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       // four are left when the tile ends and P (single-buffered) is free again before the next tile's first chunk lands
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        mbar_wait(&p_full[half], j & 1);
+        mbar_wait_backoff(&p_full[half], j & 1);
         if (half == 0) mbar_wait(&v_full[stage], (j / kKVStages) & 1);
         tc_fence_after();
         if (half == 0) ATRACE(2, 4 * j + 1);
-        if (lane == 0) {
+        {
           const uint32_t v_base = smem_u32(smem + L::kVOff + stage * L::kTile);
+          // B = V tile, MN-major: 16 keys per MMA = 16 rows of 128 B; 64-wide d-groups are kKT*128 B apart (LBO)
+          const uint64_t vdesc0 = make_smem_desc_sw128(v_base, kKT * 128, 1024);
 #pragma unroll
           for (int k4 = 0; k4 < kKT / 32; ++k4) {
             const int ks = half * (kKT / 32) + k4;
-            // B = V tile, MN-major: 16 keys per MMA = 16 rows of 128 B; 64-wide d-groups are kKT*128 B apart (LBO)
-            umma_ts(tmem_base + L::kOCol, tmem_base + L::kPCol + ks * 8, make_smem_desc_sw128(v_base + ks * 2048, kKT * 128, 1024), idesc_pv,
-                    (j | ks) != 0 ? 1u : 0u);
+            umma_ts_elect(tmem_base + L::kOCol, tmem_base + L::kPCol + ks * 8, vdesc0 + ks * (2048 >> 4), idesc_pv, (j | ks) != 0 ? 1u : 0u);
           }
-          if (half == 1) umma_commit(pv_done);   // the V stage is released by the softmax warp that observes pv_done
+          if (half == 1) umma_commit_elect(pv_done);   // the V stage is released by the softmax warp that observes pv_done
         }
         __syncwarp();
       }

@@ -61,6 +61,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// For warps whose wait is LONG and off the critical path (a TMA producer waiting for a free stage, epilogue warps waiting for a
+// whole tile's mainloop, an MMA issuer waiting for the softmax warps): the tight try_wait + branch loop above issues an instruction
+// every few cycles and competes for the issue port of its SM sub-partition with the warp that IS on the critical path (the single
+// thread issuing tcgen05.mma, the softmax warps) -- tools/gemm_trace.py / attn_trace.py showed 115-180 cycles per issued MMA against
+// 56 in isolation.  Sleeping between polls gives those slots back; `ns` bounds the extra wake-up latency.
+#ifndef TPDM_BACKOFF_NS
+#define TPDM_BACKOFF_NS 64
+#endif
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = TPDM_BACKOFF_NS) {
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns) asm volatile("nanosleep.u32 %0;\n" ::"r"(ns));
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor), tile mode, mbarrier completion
@@ -139,6 +152,37 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// The same three for a CONVERGED warp: every lane executes the statement with identical (warp-uniform) operands and ONE elected
+// lane issues.  Inside `if (lane == 0)` the compiler cannot use the uniform datapath and wraps every UTCHMMA / UTCBAR in a
+// "waterfall" loop (ELECT, R2UR, PLOP3, BRA.U.ANY: ~13 instructions and a dependent branch per MMA, 115-180 cycles per issued MMA in
+// tools/gemm_trace.py / attn_trace.py against 56 in tools/microbench/mma_issue_rate.cu); in converged code there is no branch.
+// Measured on the CTA-pair GEMM (B200, round 2): QKV 1335 -> 1445, FF1+GELU 1272 -> 1431, FF2 1258 -> 1320 TFLOP/s.
+__device__ __forceinline__ void umma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar))
+      : "memory");
 }
 
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 A/B, A K-major; B K-major unless b_mn_major.

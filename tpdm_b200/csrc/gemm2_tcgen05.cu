@@ -24,8 +24,12 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BN2 = 256;
-constexpr int BK = 64;
-constexpr int kStages2 = 5;
+#ifndef TPDM_GEMM2_BK
+#define TPDM_GEMM2_BK 64
+#endif
+constexpr int BK = TPDM_GEMM2_BK;   // k-block per pipeline stage: 64 (one 128-byte swizzle atom row) or 128 (two, side by side)
+constexpr int kSub = BK / 64;       // 64-wide TMA boxes per operand and stage
+constexpr int kStages2 = BK == 64 ? 5 : 3;
 constexpr int kEpiWarps2 = 8;   // two warps per TMEM lane quarter, each draining half of the tile's columns
 constexpr int kThreads2 = 64 + 32 * kEpiWarps2;
 constexpr int kABytes2 = BM * BK * 2;
@@ -35,6 +39,13 @@ constexpr int kRing2 = kStages2 * kStageBytes2;
 constexpr int kEpi2 = kEpiWarps2 * 32 * kStagePad * 4 + kEpiWarps2 * 2 * (BN2 / 2) * 4;
 constexpr int kBarOff2 = kRing2 + kEpi2;
 constexpr int kSmem2 = kBarOff2 + 256 + 1024;
+
+// -DTPDM_GEMM_TRACE: clock64() stamps of the leader CTA's MMA warp (cluster 0): per k-block {before the full-barrier wait, after it,
+// after the issue + commit}, and per tile the wait for a free accumulator; read back with tpdm_gemm_trace_read (tools/gemm_trace.py)
+#ifdef TPDM_GEMM_TRACE
+__device__ long long g_gemm_trace[4096];
+__device__ int g_gemm_trace_n;
+#endif
 
 struct Gemm2Params {
   GemmOp op[2];
@@ -105,6 +116,27 @@ __device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint6
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same two instructions for a CONVERGED warp: every lane executes the statement with identical (warp-uniform) operands and one
+// elected lane issues.  Inside `if (lane == 0)` the compiler cannot use the uniform datapath and wraps every UTCHMMA in a
+// "waterfall" loop (ELECT / R2UR / PLOP3 / BRA.U.ANY, ~13 instructions and a dependent branch per MMA); in converged code the
+// descriptors live in uniform registers and an MMA costs a UIADD3 or two.
+__device__ __forceinline__ void umma2_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
 // arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have retired
 __device__ __forceinline__ void umma2_commit_multicast(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
@@ -169,13 +201,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
         const int m0 = tc.mtp * 2 * BM + static_cast<int>(rank) * BM;
         const int nb0 = tc.nt * BN2 + static_cast<int>(rank) * (BN2 / 2);
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kStageBytes2;
           uint8_t* sB = sA + kABytes2;
           const uint32_t leader_full = map_to_cta(&full_bar[stage], 0);
           mbar_arrive_expect_tx_cluster(leader_full, kStageBytes2);
-          tma2_load_3d(sA, &G.tmA, leader_full, kb * BK, m0, tc.b);
-          tma2_load_2d(sB, &G.tmB2, leader_full, kb * BK, nb0);
+#pragma unroll
+          for (int h = 0; h < kSub; ++h) {
+            tma2_load_3d(sA + h * (BM * 128), &G.tmA, leader_full, kb * BK + h * 64, m0, tc.b);
+            tma2_load_2d(sB + h * ((BN2 / 2) * 128), &G.tmB2, leader_full, kb * BK + h * 64, nb0);
+          }
           if (++stage == kStages2) {
             stage = 0;
             phase ^= 1;
@@ -196,24 +231,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
         if (P.bmask != nullptr && P.bmask[tc.b % P.bslots] == 0) continue;
         const GemmOp& G = P.op[tc.g];
         const int nkb = (G.K + BK - 1) / BK;
+#ifdef TPDM_GEMM_TRACE
+        const bool tr = cluster_id == 0 && lane == 0;
+        long long tq0 = 0;
+        if (tr) tq0 = clock64();
+#endif
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
+#ifdef TPDM_GEMM_TRACE
+        if (tr && g_gemm_trace_n + 4 <= 4096) {
+          g_gemm_trace[g_gemm_trace_n++] = -1;          // tile marker
+          g_gemm_trace[g_gemm_trace_n++] = tq0;
+          g_gemm_trace[g_gemm_trace_n++] = clock64();
+          g_gemm_trace[g_gemm_trace_n++] = nkb;
+        }
+#endif
         const uint32_t d_tmem = tmem_base + acc * BN2;
         for (int kb = 0; kb < nkb; ++kb) {
+#ifdef TPDM_GEMM_TRACE
+          long long t0 = 0, t1 = 0;
+          if (tr) t0 = clock64();
+#endif
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+#ifdef TPDM_GEMM_TRACE
+          if (tr) t1 = clock64();
+#endif
+          {
             const uint32_t a_base = smem_u32(smem + stage * kStageBytes2);
             const uint32_t b_base = a_base + kABytes2;
+            // descriptors of the stage once; the sixteen-element k steps advance the 14-bit start-address field (units of 16 B)
+            const uint64_t adesc0 = make_smem_desc_sw128(a_base, 16, 1024), bdesc0 = make_smem_desc_sw128(b_base, 16, 1024);
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t adesc = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-              const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-              umma2_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              const uint32_t ao = ((k / 4) * (BM * 128) + (k % 4) * 32) >> 4, bo = ((k / 4) * ((BN2 / 2) * 128) + (k % 4) * 32) >> 4;
+              umma2_ss_elect(d_tmem, adesc0 + ao, bdesc0 + bo, idesc, (kb | k) != 0 ? 1u : 0u);
             }
-            umma2_commit_multicast(&empty_bar[stage]);
-            if (kb == nkb - 1) umma2_commit_multicast(&tmem_full[acc]);
+            umma2_commit_multicast_elect(&empty_bar[stage]);
+            if (kb == nkb - 1) umma2_commit_multicast_elect(&tmem_full[acc]);
           }
+#ifdef TPDM_GEMM_TRACE
+          if (tr && g_gemm_trace_n + 3 <= 4096) {
+            g_gemm_trace[g_gemm_trace_n++] = t0;
+            g_gemm_trace[g_gemm_trace_n++] = t1;
+            g_gemm_trace[g_gemm_trace_n++] = clock64();
+          }
+#endif
           __syncwarp();
           if (++stage == kStages2) {
             stage = 0;
@@ -244,7 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
       const int row_base = tc.mtp * 2 * BM + static_cast<int>(rank) * BM + q * 32;
       gemm_epilogue_tile<BN2>(
           G, tc.b, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2, st, sbias, lane, hh * (BN2 / 64), (hh + 1) * (BN2 / 64),
-          [&]() { mbar_wait(&tmem_full[acc], acc_phase); },
+          [&]() { mbar_wait_backoff(&tmem_full[acc], acc_phase); },
           [&]() {
             if (lane == 0) mbar_arrive_cluster(map_to_cta(&tmem_empty[acc], 0));
           });
@@ -262,6 +325,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) gemm2_
 }
 
 }  // namespace
+
+#ifdef TPDM_GEMM_TRACE
+extern "C" int tpdm_gemm_trace_read(long long* host, int* n, int reset) {
+  int cnt = 0;
+  if (cudaMemcpyFromSymbol(&cnt, g_gemm_trace_n, sizeof(int)) != cudaSuccess) return -1;
+  if (cudaMemcpyFromSymbol(host, g_gemm_trace, sizeof(long long) * 4096) != cudaSuccess) return -1;
+  *n = cnt;
+  if (reset) {
+    cnt = 0;
+    cudaMemcpyToSymbol(g_gemm_trace_n, &cnt, sizeof(int));
+  }
+  return 0;
+}
+#endif
 
 int gemm2_launch(const GemmOp* ops, int n_ops, cudaStream_t stream) {
   TPDM_CHECK(n_ops >= 1 && n_ops <= 2, TPDM_ERR_ARG, "gemm2_launch: 1 or 2 ops per launch");

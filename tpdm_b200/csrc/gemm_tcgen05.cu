@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
         const int nkb_all = (G.K + BK - 1) / BK, kps = (nkb_all + G.ksplit - 1) / G.ksplit;
         const int kb0 = tc.ks * kps, nkb = kb0 + kps < nkb_all ? kb0 + kps : nkb_all;
         for (int kb = kb0; kb < nkb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * L::kStageBytes;
           uint8_t* sB = sA + kABytes;
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
@@ -182,17 +182,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       for (int kb = kb0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
+          // converged warp, one elected lane per instruction (umma_ss_elect in common.cuh): no waterfall loop around the MMAs
           const uint32_t a_base = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t b_base = a_base + kABytes;
+          const uint64_t adesc0 = make_smem_desc_sw128(a_base, 16, 1024), bdesc0 = make_smem_desc_sw128(b_base, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t bdesc = make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_ss(d_tmem, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss_elect(d_tmem, adesc0 + ((k * 32) >> 4), bdesc0 + ((k * 32) >> 4), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+          umma_commit_elect(&empty_bar[stage]);
+          if (kb == nkb - 1) umma_commit_elect(&tmem_full[acc]);
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -220,7 +219,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_bf16_tcgen05_kernel(cons
       const int row_base = tc.mt * BM + q * 32;
       gemm_epilogue_tile<BN>(
           G, tc.b + tc.ks * G.batch, row_base, n0, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN, st, sbias, lane, 0, BN / 32,
-          [&]() { mbar_wait(&tmem_full[acc], acc_phase); }, [&]() { if (lane == 0) mbar_arrive(&tmem_empty[acc]); });
+          [&]() { mbar_wait_backoff(&tmem_full[acc], acc_phase); }, [&]() { if (lane == 0) mbar_arrive(&tmem_empty[acc]); });
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;

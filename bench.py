@@ -699,7 +699,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"])
     ap.add_argument("--slots", type=int, default=2, help="config3: prompts in flight per GPU")
     ap.add_argument("--prompts-per-gpu", type=int, default=8, help="config3")
-    ap.add_argument("--schedule", default="fifo", choices=["fifo"], help="config3: ticket order")
+    ap.add_argument("--schedule", default="fifo", choices=["fifo", "lpt"], help="config3: ticket order (lpt: longest expected trajectory first)")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = {"config2": 8, "config3": 2, "config4": 2}[args.workload]

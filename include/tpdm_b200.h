@@ -255,10 +255,16 @@ int tpdm_adamw_step(float* params, const float* grads, float* m, float* v, long 
  *   prompts this plan did not process are left untouched), out_steps [P], out_sigmas [P][max_steps + 1] or NULL.
  * ---------------------------------------------------------------------------------------------------------------- */
 size_t tpdm_queue_workspace_bytes(const tpdm_plan* plan, int n_prompts);
+/*   Scheduling (all optional): `order` [n_queued] maps ticket t to prompt order[t] (NULL: t), so that a caller can hand out the
+ *   prompts longest-expected-first; only the first n_queued tickets exist (<= 0: all n_prompts).  `init_sigma` [P] + `init_step` > 0:
+ *   every prompt enters the queue after init_step probe steps made elsewhere -- latents_all then holds the latents AFTER those
+ *   steps, init_sigma the sigma they reached, and out_sigmas[prompt][0..init_step] must have been filled by the caller.
+ * ---------------------------------------------------------------------------------------------------------------- */
 int tpdm_queue_begin(tpdm_plan* plan, int n_prompts, const float* latents_all, const float* neg_embeds_all,
                      const float* pos_embeds_all, const float* neg_pooled_all, const float* pos_pooled_all,
                      float guidance_scale, void* queue_workspace, size_t queue_workspace_bytes, int* ticket,
-                     float* out_latents, int* out_steps, float* out_sigmas, void* stream);
+                     float* out_latents, int* out_steps, float* out_sigmas, const int* order, int n_queued,
+                     const float* init_sigma, int init_step, void* stream);
 /* one denoising step of every occupied slot, then retire / refill.  No host synchronisation. */
 int tpdm_queue_step(tpdm_plan* plan, void* stream);
 /* the same step replayed from a CUDA graph captured on the first call (stream must not be the legacy default stream) */

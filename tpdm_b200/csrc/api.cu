@@ -78,6 +78,9 @@ struct tpdm_plan {
     float *ctx0_all = nullptr, *text_all = nullptr, *sigma_cur = nullptr, *sigma_next = nullptr, *out_latents = nullptr, *out_sigmas = nullptr;
     int *slot_prompt = nullptr, *slot_step = nullptr, *slot_flush = nullptr, *slot_load = nullptr, *slot_active = nullptr, *ticket = nullptr,
         *out_steps = nullptr, *active = nullptr, *idle_flag = nullptr;
+    const int* order = nullptr;
+    const float* init_sigma = nullptr;
+    int init_step = 0, n_queued = 0;
     cudaGraphExec_t graph = nullptr;   // one captured queue step (every pointer of a queue step is fixed between steps)
     long long graph_launches = 0;
   } q;
@@ -591,8 +594,11 @@ QueueArgs queue_args(const tpdm_plan* p, int init) {
   a.out_sigmas = q.out_sigmas;
   a.active = q.active;
   a.idle_flag = q.idle_flag;
+  a.order = q.order;
+  a.init_sigma = q.init_sigma;
+  a.init_step = q.init_step;
   a.B = p->B;
-  a.n_prompts = q.n_prompts;
+  a.n_prompts = q.n_queued;
   a.max_steps = p->max_steps;
   a.relative = p->ctx->cfg.relative;
   a.prediction_type = p->ctx->cfg.prediction_type;
@@ -616,13 +622,18 @@ size_t tpdm_queue_workspace_bytes(const tpdm_plan* p, int n_prompts) {
 
 int tpdm_queue_begin(tpdm_plan* p, int n_prompts, const float* latents_all, const float* neg_embeds_all, const float* pos_embeds_all,
                      const float* neg_pooled_all, const float* pos_pooled_all, float guidance_scale, void* queue_workspace,
-                     size_t queue_workspace_bytes, int* ticket, float* out_latents, int* out_steps, float* out_sigmas, void* stream) {
+                     size_t queue_workspace_bytes, int* ticket, float* out_latents, int* out_steps, float* out_sigmas, const int* order,
+                     int n_queued, const float* init_sigma, int init_step, void* stream) {
   TPDM_CHECK(p && latents_all && neg_embeds_all && pos_embeds_all && neg_pooled_all && pos_pooled_all && queue_workspace && ticket &&
                  out_latents && out_steps,
              TPDM_ERR_ARG, "tpdm_queue_begin: null argument");
   TPDM_CHECK(p->cfg_pairs, TPDM_ERR_STATE, "tpdm_queue_begin: the plan was created without cfg_pairs");
   TPDM_CHECK(p->ctx->has_mmdit && p->ctx->has_tpm, TPDM_ERR_STATE, "tpdm_queue_begin: needs both MMDiT and TimePredictor weights");
   TPDM_CHECK(n_prompts >= p->B, TPDM_ERR_ARG, "tpdm_queue_begin: %d prompts for %d slots (use a plan with fewer slots)", n_prompts, p->B);
+  TPDM_CHECK(order != nullptr || n_queued == n_prompts || n_queued <= 0, TPDM_ERR_ARG, "tpdm_queue_begin: n_queued needs an order table");
+  TPDM_CHECK(n_queued <= n_prompts, TPDM_ERR_ARG, "tpdm_queue_begin: n_queued %d exceeds the %d prompts", n_queued, n_prompts);
+  TPDM_CHECK(init_step >= 0 && init_step < p->max_steps && (init_step == 0) == (init_sigma == nullptr), TPDM_ERR_ARG,
+             "tpdm_queue_begin: init_sigma and init_step (%d) go together, init_step < max_steps", init_step);
   TPDM_CHECK((reinterpret_cast<uintptr_t>(queue_workspace) & 1023) == 0 && queue_workspace_bytes >= queue_bytes(p, n_prompts), TPDM_ERR_ARG,
              "tpdm_queue_begin: queue workspace must be 1 KiB aligned and >= %zu bytes", queue_bytes(p, n_prompts));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -647,6 +658,10 @@ int tpdm_queue_begin(tpdm_plan* p, int n_prompts, const float* latents_all, cons
   q.active = q.slot_active + B;
   q.idle_flag = q.active + 1;
   q.n_prompts = n_prompts;
+  q.n_queued = n_queued > 0 ? n_queued : n_prompts;
+  q.order = order;
+  q.init_sigma = init_sigma;
+  q.init_step = init_step;
   q.noise_all = latents_all;
   q.ticket = ticket;
   q.out_latents = out_latents;

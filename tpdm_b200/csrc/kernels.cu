@@ -826,12 +826,12 @@ __global__ void queue_advance_kernel(const QueueArgs a) {
     }
     if (need) {
       const int t = atomicAdd_system(a.ticket, 1);
-      prompt = t < a.n_prompts ? t : -1;
+      prompt = t < a.n_prompts ? (a.order ? a.order[t] : t) : -1;
       a.slot_prompt[i] = prompt;
-      a.slot_step[i] = 0;
-      a.sigma_cur[i] = 1.0f;                            // sigma = ones (:508)
+      a.slot_step[i] = a.init_step;
+      a.sigma_cur[i] = (a.init_sigma && prompt >= 0) ? a.init_sigma[prompt] : 1.0f;   // sigma = ones (:508) unless probed
       load = prompt >= 0 ? 1 : 0;
-      if (prompt >= 0 && a.out_sigmas) a.out_sigmas[static_cast<long long>(prompt) * (a.max_steps + 1)] = 1.0f;
+      if (prompt >= 0 && a.out_sigmas && a.init_step == 0) a.out_sigmas[static_cast<long long>(prompt) * (a.max_steps + 1)] = 1.0f;
     }
     a.slot_flush[i] = flush;
     a.slot_load[i] = load;

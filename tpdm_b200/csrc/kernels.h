@@ -96,6 +96,9 @@ struct QueueArgs {
   float* out_sigmas;         // [P][max_steps + 1] or null
   int* active;               // [1] slots that hold a prompt after this step
   int* idle_flag;            // [1] 1 when active == 0 (skip flag of the next, speculatively enqueued step)
+  const int* order;          // [n_prompts] ticket -> prompt id (longest-expected-first scheduling), or null: ticket == prompt id
+  const float* init_sigma;   // [P] sigma a prompt enters the queue with (after `init_step` probe steps), or null: 1
+  int init_step;             // denoising steps every prompt has already made when it enters the queue (0 without a probe)
   int B, n_prompts, max_steps, relative, prediction_type, init;
   float min_sigma, epsilon;
 };

@@ -368,6 +368,62 @@ class Engine:
             out["velocities"] = vel[:, :T]
         return out
 
+    def _probe_and_order(self, lat, pe, ne, pp, npp, guidance_scale, max_steps, out_lat, out_steps, out_sig):
+        """Longest-expected-first scheduling for the device queue.  Greedy list scheduling loses the tail: the last GPUs to finish
+        are whoever drew a long prompt late (86.6 % of the sum-of-steps / N bound on 8 GPUs, profiles/r01_config3_devq_n8.log).
+        Trajectory lengths are not known in advance, but the FIRST TimePredictor call already says how fast sigma falls for a
+        prompt.  So every GPU runs denoising step 0 for its static share of the prompts (one batched call; the step is not wasted:
+        it IS step 0 of those trajectories), the post-step latents and sigmas are all-gathered (1 MB per prompt over NVLink -- the
+        one exchange of this scheduler, a few hundred microseconds), every rank sorts the prompts by the expected number of
+        remaining steps, ceil(log(min_sigma / sigma_1) / log(sigma_1)), and the queue hands them out longest first with every
+        prompt entering at step 1.  Ticket claiming stays dynamic, so a wrong estimate costs balance, never correctness: each
+        prompt still follows exactly its own trajectory.  Returns (latents after step 0 [P], order, n_queued, sigma_1 [P])."""
+        import math
+
+        import torch.distributed as dist
+
+        lib = L.load()
+        P = lat.shape[0]
+        dev = self.device
+        world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        if P % world != 0:
+            raise ValueError(f"schedule='lpt' needs the number of prompts ({P}) to be a multiple of the number of ranks ({world})")
+        mine = torch.arange(rank, P, world, device=dev)
+        nb = mine.numel()
+        plan = self.plan(nb, True, lat.shape[-1], pe.shape[1], 1)
+        st = plan.state
+        sel = lambda t: t[mine].contiguous()
+        l0, pe0, ne0, pp0, npp0 = sel(lat), sel(pe), sel(ne), sel(pp), sel(npp)
+        with torch.cuda.device(dev):
+            stream = L.stream_ptr()
+            L.check(lib.tpdm_sample_begin(plan.handle, L.ptr(l0), L.ptr(ne0), L.ptr(pe0), L.ptr(npp0), L.ptr(pp0), float(guidance_scale), 1, None,
+                                          0, stream))
+            L.check(lib.tpdm_sample_step(plan.handle, 0, stream))
+        packed = torch.cat([st["latents"].reshape(nb, -1), st["sigma_hist"][:, 1:2]], dim=1).contiguous()     # (nb, C*h*w + 1)
+        if world > 1:
+            allp = torch.empty(world, nb, packed.shape[1], device=dev, dtype=packed.dtype)
+            dist.all_gather_into_tensor(allp, packed)
+            allp = allp.permute(1, 0, 2).reshape(P, -1)          # prompt p = rank + k * world  ->  row k * world + rank = p
+        else:
+            allp = packed
+        lat1 = allp[:, :-1].reshape(lat.shape).contiguous()
+        sig1 = allp[:, -1].contiguous()
+        done = sig1 < self.min_sigma                              # the whole trajectory was one step (:608)
+        r = sig1.clamp(1e-6, 1 - 1e-6)
+        est = torch.ceil(math.log(self.min_sigma) / torch.log(r) - 1.0).clamp(0, max_steps - 1)
+        est = torch.where(done, torch.full_like(est, -1.0), est)
+        order = torch.argsort(est, descending=True, stable=True).to(torch.int32).contiguous()
+        n_queued = int((~done).sum().item())
+        out_sig[:, 0] = 1.0
+        out_sig[:, 1] = sig1
+        probed_here = torch.zeros(P, dtype=torch.bool, device=dev)
+        probed_here[mine] = True
+        fin = done & probed_here                                  # finished at the probe: reported by the rank that ran it
+        out_steps[fin] = 1
+        out_lat[fin] = lat1[fin]
+        return lat1, order, n_queued, sig1
+
     def sample_queue(self, latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
                      slots: int, max_inference_steps: int, guidance_scale: float, ticket: Optional[torch.Tensor] = None,
                      out_latents: Optional[torch.Tensor] = None, use_graph: bool = True, schedule: str = "fifo"):
@@ -378,11 +434,10 @@ class Engine:
         lib = L.load()
         P, Cc, h, w = latents.shape
         dev, f32 = self.device, torch.float32
-        if schedule != "fifo":
-            raise ValueError(f"unknown queue schedule {schedule!r} (tickets are handed out in prompt order: 'fifo')")
+        if schedule not in ("fifo", "lpt"):
+            raise ValueError(f"unknown queue schedule {schedule!r} ('fifo': tickets in prompt order, 'lpt': longest expected trajectory first)")
         if not 1 <= slots <= P:
             raise ValueError(f"slots must be in [1, {P}]")
-        plan = self.plan(slots, True, h, prompt_embeds.shape[1], max_inference_steps)
         cvt = lambda t: t.to(device=dev, dtype=f32).contiguous()
         lat, pe, ne, pp, npp = cvt(latents), cvt(prompt_embeds), cvt(negative_prompt_embeds), cvt(pooled_prompt_embeds), cvt(negative_pooled_prompt_embeds)
         if ticket is None:
@@ -390,6 +445,14 @@ class Engine:
         out_lat = torch.zeros(P, Cc, h, w, device=dev, dtype=f32) if out_latents is None else out_latents
         out_steps = torch.zeros(P, dtype=torch.int32, device=dev)
         out_sig = torch.zeros(P, max_inference_steps + 1, device=dev, dtype=f32)
+        order = init_sigma = None
+        n_queued, init_step = P, 0
+        if schedule == "lpt" and max_inference_steps > 1:
+            lat, order, n_queued, init_sigma = self._probe_and_order(lat, pe, ne, pp, npp, guidance_scale, max_inference_steps, out_lat, out_steps, out_sig)
+            init_step = 1
+            if n_queued == 0:       # every trajectory ended at its first step
+                return dict(latents=out_lat, steps=out_steps, sigmas=out_sig, device_steps=1)
+        plan = self.plan(slots, True, h, prompt_embeds.shape[1], max_inference_steps)
         nbytes = lib.tpdm_queue_workspace_bytes(plan.handle, P)
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=dev)
         base = (ws.data_ptr() + 1023) // 1024 * 1024
@@ -403,7 +466,9 @@ class Engine:
         with torch.cuda.device(dev), torch.cuda.stream(qs):
             stream = L.stream_ptr()
             L.check(lib.tpdm_queue_begin(plan.handle, P, L.ptr(lat), L.ptr(ne), L.ptr(pe), L.ptr(npp), L.ptr(pp), float(guidance_scale), base,
-                                         nbytes, ticket.data_ptr(), L.ptr(out_lat), L.ptr(out_steps), L.ptr(out_sig), stream))
+                                         nbytes, ticket.data_ptr(), L.ptr(out_lat), L.ptr(out_steps), L.ptr(out_sig),
+                                         L.ptr(order) if order is not None else None, int(n_queued),
+                                         L.ptr(init_sigma) if init_sigma is not None else None, int(init_step), stream))
             act_p, slot_p = L.vp(), L.vp()
             L.check(lib.tpdm_queue_status(plan.handle, C.byref(act_p), C.byref(slot_p)))
             off = act_p.value - ws.data_ptr()          # the counters live in the queue workspace
@@ -431,5 +496,5 @@ class Engine:
                     raise RuntimeError("sample_queue: the queue did not drain within the step bound")
             torch.cuda.current_stream().synchronize()
         torch.cuda.current_stream(dev).wait_stream(qs)
-        self._queue_keepalive = (ws, lat, pe, ne, pp, npp, ticket)
-        return dict(latents=out_lat, steps=out_steps, sigmas=out_sig, device_steps=steps_run)
+        self._queue_keepalive = (ws, lat, pe, ne, pp, npp, ticket, order, init_sigma)
+        return dict(latents=out_lat, steps=out_steps, sigmas=out_sig, device_steps=steps_run + (1 if init_step else 0))

@@ -79,6 +79,24 @@ def test_sd3_vae_decode_1024_properties():
     assert not torch.equal(b[0], b[1])
 
 
+def test_sd3_vae_decode_1024_matches_oracle():
+    """The full-size image itself (128x128 latent -> 1024^2) against the fp32 oracle on the same GPU: image rel-L2 and uint8 pixels."""
+    from oracle import vae_oracle as V
+
+    ora, vae = _pair(V.sd3_vae_config())
+    g = torch.Generator(device="cuda").manual_seed(11)
+    lat = torch.randn(1, 16, 128, 128, device="cuda", generator=g)
+    with torch.no_grad():
+        ref = ora.decode_latents(lat)
+    img = vae.decode_latents(lat, "pt")
+    assert img.shape == ref.shape == (1, 3, 1024, 1024)
+    err = rel(img, ref)
+    print(f"[vae 1024^2] image rel-L2 {err:.2e}")
+    assert err < IMG_TOL
+    diff = (vae.decode_latents(lat, "uint8").int() - V.postprocess_uint8(ref).int()).abs()
+    assert int(diff.max()) <= 6 and float(diff.float().mean()) < 0.5
+
+
 def test_pipeline_returns_images_when_vae_attached():
     """modeling_sd3_pnt.py:645-655: with a VAE the pipeline output carries one [PIL image] list per prompt, decoded from
     the last valid latent of each trajectory."""

@@ -71,6 +71,25 @@ def test_dynamic_queue_world_size_2():
     assert {merged[i]["rank"] for i in merged} == {0, 1}
 
 
+def test_longest_expected_first_order():
+    """The ticket order of the device queue's 'lpt' schedule: estimates from the sigma after the first step, longest first, stable."""
+    from tpdm_b200.work_queue import expected_remaining_steps, longest_first_order
+
+    s1 = torch.tensor([0.73, 0.30, 0.95, 0.0005, 0.73, 0.50])
+    est = expected_remaining_steps(s1, min_sigma=1e-3, max_steps=28)
+    # a constant ratio of 0.73 needs 22 steps to get below 1e-3 (0.73^22 = 9.8e-4): 21 more after the first
+    assert est.tolist() == [21.0, 5.0, 27.0, -1.0, 21.0, 9.0]
+    order = longest_first_order(est).tolist()
+    assert order == [2, 0, 4, 5, 1, 3]                  # slowest schedule first, ties in prompt order, the finished prompt last
+    # list scheduling with that order never does worse than prompt order on this instance (2 workers)
+    def makespan(seq):
+        load = [0.0, 0.0]
+        for i in seq:
+            load[load.index(min(load))] += float(est[i]) + 1
+        return max(load)
+    assert makespan(order[:-1]) <= makespan([0, 1, 2, 4, 5])
+
+
 def test_queue_without_process_group():
     q = PromptQueue(3)
     assert list(q) == [0, 1, 2] and q.claim() is None

@@ -331,8 +331,12 @@ class Engine:
             rec = torch.empty(B, max_inference_steps, g, g, 2 * self.D, device=dev, dtype=torch.bfloat16)
         if record_velocity:
             vel = torch.empty(B, max_inference_steps, Cc, h, w, device=dev, dtype=f32)
-        done_host = torch.zeros(max_inference_steps, dtype=torch.int32).pin_memory()
-        events = []
+        done_host = getattr(self, "_done_host", None)
+        if done_host is None or done_host.numel() < max_inference_steps:
+            done_host = self._done_host = torch.zeros(max(64, max_inference_steps), dtype=torch.int32).pin_memory()
+        events = getattr(self, "_step_events", None)
+        if events is None:
+            events = self._step_events = [torch.cuda.Event(), torch.cuda.Event()]
         executed = max_inference_steps
         with torch.cuda.device(dev):
             stream = L.stream_ptr()
@@ -345,16 +349,14 @@ class Engine:
                 if vel is not None:
                     vel[:, step].copy_(st["velocity"])
                 done_host[step: step + 1].copy_(st["all_done"][step: step + 1], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record()
-                events.append(ev)
-                if step >= 1:
-                    events[step - 1].synchronize()
+                events[step & 1].record()
+                if step >= 1:       # the flag of the previous step: the device never waits for the host
+                    events[(step - 1) & 1].synchronize()
                     if int(done_host[step - 1]) != 0:
                         executed = step  # steps [0, step) are real; step `step` was skipped on the device
                         break
             else:
-                events[-1].synchronize()
+                events[(max_inference_steps - 1) & 1].synchronize()
         T = executed
         out = dict(
             steps=T,
@@ -378,8 +380,6 @@ class Engine:
         remaining steps, ceil(log(min_sigma / sigma_1) / log(sigma_1)), and the queue hands them out longest first with every
         prompt entering at step 1.  Ticket claiming stays dynamic, so a wrong estimate costs balance, never correctness: each
         prompt still follows exactly its own trajectory.  Returns (latents after step 0 [P], order, n_queued, sigma_1 [P])."""
-        import math
-
         import torch.distributed as dist
 
         lib = L.load()
@@ -409,11 +409,10 @@ class Engine:
             allp = packed
         lat1 = allp[:, :-1].reshape(lat.shape).contiguous()
         sig1 = allp[:, -1].contiguous()
+        from .work_queue import expected_remaining_steps, longest_first_order
+
         done = sig1 < self.min_sigma                              # the whole trajectory was one step (:608)
-        r = sig1.clamp(1e-6, 1 - 1e-6)
-        est = torch.ceil(math.log(self.min_sigma) / torch.log(r) - 1.0).clamp(0, max_steps - 1)
-        est = torch.where(done, torch.full_like(est, -1.0), est)
-        order = torch.argsort(est, descending=True, stable=True).to(torch.int32).contiguous()
+        order = longest_first_order(expected_remaining_steps(sig1, self.min_sigma, max_steps)).contiguous()
         n_queued = int((~done).sum().item())
         out_sig[:, 0] = 1.0
         out_sig[:, 1] = sig1

@@ -46,6 +46,24 @@ class PromptQueue:
             yield idx
 
 
+def expected_remaining_steps(sigma_after_first_step: torch.Tensor, min_sigma: float, max_steps: int) -> torch.Tensor:
+    """Length estimate behind the longest-expected-first ticket order of the device queue (Engine._probe_and_order): a prompt whose
+    first step took sigma from 1 to s keeps multiplying by about s, so it needs ceil(log(min_sigma / s) / log(s)) more steps until
+    sigma_next < min_sigma (modeling_sd3_pnt.py:608), at most max_steps - 1; -1 marks a trajectory that already ended at its first step."""
+    import math
+
+    s = sigma_after_first_step.float()
+    done = s < min_sigma
+    r = s.clamp(1e-6, 1 - 1e-6)
+    est = torch.ceil(math.log(min_sigma) / torch.log(r) - 1.0).clamp(0, max_steps - 1)
+    return torch.where(done, torch.full_like(est, -1.0), est)
+
+
+def longest_first_order(estimates: torch.Tensor) -> torch.Tensor:
+    """Ticket t -> prompt id, longest expected trajectory first (stable, so every rank computes the same table); finished prompts last."""
+    return torch.argsort(estimates, descending=True, stable=True).to(torch.int32)
+
+
 def static_shard(n_prompts: int, rank: int, world: int) -> List[int]:
     """Round-robin split (what the bench's weak-scaling run uses: every rank owns prompts rank, rank+world, ...)."""
     return list(range(rank, n_prompts, world))

@@ -17,8 +17,10 @@ using namespace tpdm;
 // back while the MMAs are being issued: does a busy sub-partition slow the issuing thread down?
 // `commit_every` > 0: a tcgen05.commit (mbarrier arrive on completion) after every commit_every MMAs, as a pipelined kernel issues
 // them -- does the commit cost the issuing thread time?
+// `converged` != 0: the MMAs are issued by the whole (converged) warp with the lane election inside the asm statement
+// (umma_ss_elect / umma_ts_elect in common.cuh) instead of from inside `if (lane == 0)`: no waterfall loop around UTCHMMA.
 template <int MODE, int N>
-__global__ void __launch_bounds__(256) k(uint32_t* out, int n_mma, int issuers, int hammer, int commit_every = 0) {
+__global__ void __launch_bounds__(256) k(uint32_t* out, int n_mma, int issuers, int hammer, int commit_every = 0, int converged = 0) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar[2];
@@ -71,7 +73,17 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, int n_mma, int issuers, 
     const uint32_t dcol = tmem + (warp * (N <= 64 ? 64 : 0));    // distinct accumulators when they fit (N = 64), else a shared one
     __syncwarp();
     t0 = clock64();
-    if (lane == 0) {
+    if (converged) {
+      for (int i = 0; i < n_mma; ++i) {
+        const uint32_t off = (i & 3) * 32;
+        if (MODE == 0)
+          umma_ss_elect(dcol, make_smem_desc_sw128(a_base + off, 16, 1024), make_smem_desc_sw128(b_base + off, 16, 1024), idesc, i ? 1u : 0u);
+        else
+          umma_ts_elect(dcol, tmem + 192 + (i & 3) * 8, make_smem_desc_sw128(b_base + off, 16, 1024), idesc, i ? 1u : 0u);
+      }
+      t1 = clock64();
+      umma_commit_elect(&bar[warp]);
+    } else if (lane == 0) {
       for (int i = 0; i < n_mma; ++i) {
         const uint32_t off = (i & 3) * 32;
         if (MODE == 0)
@@ -103,12 +115,12 @@ __global__ void __launch_bounds__(256) k(uint32_t* out, int n_mma, int issuers, 
 }
 
 template <int MODE, int N>
-void run(const char* name, uint32_t* d, int ctas_per_sm, int issuers, int hammer = 0, int commit_every = 0) {
+void run(const char* name, uint32_t* d, int ctas_per_sm, int issuers, int hammer = 0, int commit_every = 0, int converged = 0) {
   const int n_mma = 256;
   const size_t smem = 16384 + 32768 + 1024;
   cudaFuncSetAttribute(k<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   for (int rep = 0; rep < 2; ++rep) {
-    k<MODE, N><<<148 * ctas_per_sm, 256, smem>>>(d, n_mma, issuers, hammer, commit_every);
+    k<MODE, N><<<148 * ctas_per_sm, 256, smem>>>(d, n_mma, issuers, hammer, commit_every, converged);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
       printf("%s: %s\n", name, cudaGetErrorString(e));
@@ -119,6 +131,7 @@ void run(const char* name, uint32_t* d, int ctas_per_sm, int issuers, int hammer
   cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
   const double floor_clk = 128.0 * N / 256.0;   // tensor-pipe cycles of one M=128, K=16 MMA at full rate
   if (commit_every) printf("[commit after every %d MMAs] ", commit_every);
+  if (converged) printf("[converged warp, elected lane] ");
   printf("%s%-4s N=%3d  %d CTA/SM x %d issuer(s): issue %6.1f clk/MMA, issue+drain %6.1f clk/MMA  (full-rate pipe time %4.0f clk/MMA; SM share "
          "%4.0f)\n",
          hammer ? "[4 MUFU-bound warps per CTA] " : "", name, N, ctas_per_sm, issuers, h[0] / double(n_mma), h[1] / double(n_mma), floor_clk, floor_clk * ctas_per_sm * issuers);
@@ -134,6 +147,13 @@ int main() {
       run<0, 128>("SS", d, ctas, iss);
       run<1, 128>("TS", d, ctas, iss);
       if (iss == 1) run<0, 256>("SS", d, ctas, iss);
+    }
+  for (int ctas = 1; ctas <= 2; ++ctas)
+    for (int iss = 1; iss <= 2; ++iss) {
+      run<0, 64>("SS", d, ctas, iss, 0, 0, 1);
+      run<1, 64>("TS", d, ctas, iss, 0, 0, 1);
+      run<0, 128>("SS", d, ctas, iss, 0, 0, 1);
+      if (iss == 1) run<0, 256>("SS", d, ctas, iss, 0, 0, 1);
     }
   for (int ctas = 1; ctas <= 2; ++ctas)
     for (int ce = 1; ce <= 4; ce *= 2) {

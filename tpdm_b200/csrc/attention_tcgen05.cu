@@ -17,9 +17,11 @@
 // last quarter of this tile's exponentials and under P V), overlap on the SM from the second co-resident CTA.
 //
 // Why 128-key tiles (round 2; measurements in profiles/r02_*.txt):
-//  * tools/microbench/mma_issue_rate.cu: one thread cannot issue tcgen05.mma faster than one per ~56 cycles, whatever its size,
-//    and four issuers on one SM get 90-140 cycles each.  The round-1 kernel issued N = 64 MMAs (32 tensor cycles each) and its
-//    timeline (tools/attn_trace.py) showed 539 cycles per 64 keys in the Q K^T issuer alone; N = 128 halves the instruction count.
+//  * tools/microbench/mma_issue_rate.cu: an SS MMA of N = 64 cannot run faster than one per 48 cycles (its 6 KB of operands come
+//    out of shared memory at 128 B/clk) although it holds the tensor pipe for 32, N = 128 runs at the pipe rate (64); issued
+//    from inside `if (lane == 0)` -- as round 1 did -- every MMA additionally paid a waterfall loop (56-72 cycles in isolation,
+//    115-180 next to busy warps: the round-1 timeline, tools/attn_trace.py, shows 539 cycles per 64 keys in the Q K^T issuer
+//    alone).  N = 128 halves the instruction count and the MMAs are now issued by the converged warp (umma_*_elect).
 //  * the same timeline showed ~625 of the 1460 cycles a softmax warp spent per 64 keys in mbarrier round trips, exposed TMEM
 //    load latency and the P hand-over; with 128 keys per round trip that cost is halved, and the chunk loads are software
 //    pipelined (the load of chunk c+1 is in flight while chunk c is exponentiated).

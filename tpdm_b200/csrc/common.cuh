@@ -157,7 +157,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // The same three for a CONVERGED warp: every lane executes the statement with identical (warp-uniform) operands and ONE elected
 // lane issues.  Inside `if (lane == 0)` the compiler cannot use the uniform datapath and wraps every UTCHMMA / UTCBAR in a
 // "waterfall" loop (ELECT, R2UR, PLOP3, BRA.U.ANY: ~13 instructions and a dependent branch per MMA, 115-180 cycles per issued MMA in
-// tools/gemm_trace.py / attn_trace.py against 56 in tools/microbench/mma_issue_rate.cu); in converged code there is no branch.
+// tools/gemm_trace.py / attn_trace.py; tools/microbench/mma_issue_rate.cu in isolation: TS N = 64 at 65 cycles per MMA from inside
+// `if (lane == 0)` against 33 = the tensor-pipe rate from the converged warp); in converged code there is no branch.
 // Measured on the CTA-pair GEMM (B200, round 2): QKV 1335 -> 1445, FF1+GELU 1272 -> 1431, FF2 1258 -> 1320 TFLOP/s.
 __device__ __forceinline__ void umma_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

@@ -83,6 +83,8 @@ def test_joint_attention(L, Bt, S, H, d, q_rows):
     assert rel(out[:, :rows, :, :d], ref[:, :rows]) < 6e-3
     if dp > d:
         assert float(out[..., d:].float().abs().max()) == 0.0
+    # ordinary activations never leave the fast kernel (the exact kernel behind it is an empty launch)
+    assert lib.tpdm_attention_redo_count() in (0, -1)
 
 
 @pytest.mark.parametrize("jump", [10, 40, 70, 100, 300, 330, 370, 511, "ramp"])
@@ -125,6 +127,34 @@ def test_attention_extreme_logits_stay_finite(L):
     torch.cuda.synchronize()
     assert torch.isfinite(out.float()).all()
     assert rel(out, ref) < 1e-2
+    # scores this far apart cannot be kept in range by the row-sum guard of the fast kernel: its CTAs must have been flagged and
+    # recomputed by the exact kernel (per-chunk maxima)
+    n_redo = lib.tpdm_attention_redo_count()
+    assert n_redo == -1 or n_redo > 0, n_redo
+
+
+@pytest.mark.parametrize("scale_k", [2.0, 3.0, 4.5])
+def test_attention_row_sum_guard_moves_the_reference(L, scale_k):
+    """Keys whose scores grow steadily (a few 2^10 per 128-key tile) are handled INSIDE the fast kernel: the row sum crosses 2^32
+    at the top of a tile and the reference is moved by floor(log2 l) (O and l rescaled) -- no tile is handed to the exact kernel."""
+    torch.manual_seed(5)
+    lib = L.load()
+    Bt, S, H, d = 1, 1024, 2, 64
+    qkv = torch.randn(Bt, S, 3, H, d, device="cuda")
+    qkv[:, :, 0] = qkv[:, :, 0].abs() * 2.0                     # q >= 0 ...
+    qkv[:, :, 1] = qkv[:, :, 1].abs() * torch.linspace(0.05, scale_k, S, device="cuda").view(1, S, 1, 1)   # ... k >= 0 and growing
+    qkv = qkv.bfloat16().contiguous()
+    out = torch.zeros(Bt, S, H, d, device="cuda", dtype=torch.bfloat16)
+    q, k, v = (qkv[:, :, i].float().transpose(1, 2) for i in range(3))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2)
+    spread = (q @ k.transpose(-1, -2) * (1.4427 / 8)).amax(-1) - (q @ k[:, :, :128].transpose(-1, -2) * (1.4427 / 8)).amax(-1)
+    assert float(spread.max()) > 40.0       # log2 units above the first tile's maximum: the guard has to act
+    L.check(lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, 64, d, 0, None))
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 1e-2
+    n_redo = lib.tpdm_attention_redo_count()
+    assert n_redo in (0, -1), n_redo
 
 
 def test_tcgen05_kernels_are_bit_reproducible(L):

@@ -38,6 +38,11 @@ for j in range(4, n_kv - 2):
     if 10 <= j < 16:
         print(f"  j={j:3d}: " + "  ".join(f"{names[k]}={ph[k]:4d}" for k in range(5)) + f"  | period={ph[5]}")
 print("mean over", cnt, "tiles: " + "  ".join(f"{names[k]}={tot[k] / cnt:6.1f}" for k in range(5)) + f"  | period={tot[5] / cnt:.1f}")
+sub = [(sm[8 * j + 6] - sm[8 * j + 2], sm[8 * j + 7] - sm[8 * j + 6], sm[8 * j + 3] - sm[8 * j + 7]) for j in range(4, n_kv - 2)
+       if sm[8 * j + 2] and sm[8 * j + 6] and sm[8 * j + 7] and sm[8 * j + 3]]
+if sub:
+    m = [sum(x[k] for x in sub) / len(sub) for k in range(3)]
+    print(f"inside 'max + chunk 0': max of chunk 0 + vote {m[0]:.0f}, exponentials up to the end of the pv_done wait {m[1]:.0f}, P store + next load + vote {m[2]:.0f}")
 for role, name, arr in ((1, "QK issuer", qk), (2, "PV issuer", pv)):
     w = s_ = c = 0.0
     for j in range(4, n_kv - 2):

@@ -768,6 +768,8 @@ int tpdm_joint_attention(const void* qkv, void* out, int Bt, int S, int H, int d
   return attn_launch(&op, static_cast<cudaStream_t>(stream));
 }
 
+int tpdm_attention_redo_count(void) { return attn_redo_count(); }
+
 int tpdm_conv3x3_nhwc(const void* x, const void* w, const float* bias, float* out, int batch, int g, int C, int N, void* stream) {
   TPDM_CHECK(x && w && out, TPDM_ERR_ARG, "tpdm_conv3x3_nhwc: null argument");
   GemmOp op;

@@ -34,6 +34,8 @@
 // to 2^32 above the reference costs no precision, and the final 1/l cancels the reference.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -84,7 +86,7 @@ struct AttnSmem {
   static constexpr uint32_t kOCol = 192;   // O: DP columns
 };
 
-template <int DP>
+template <int DP, bool kFast>
 __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attention_tcgen05_kernel(const __grid_constant__ AttnOp A) {
   using L = AttnSmem<DP>;
   pdl_launch_dependents();
@@ -134,6 +136,13 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   pdl_wait();
   if (A.skip != nullptr && *A.skip != 0) return;
   if (A.bmask != nullptr && A.bmask[blockIdx.z % A.bslots] == 0) return;  // emptied queue slot
+  // fast kernel: this CTA's "redo" flag starts at 0; exact kernel launched behind it: only flagged CTAs run (see attn_launch)
+  const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  if constexpr (kFast) {
+    if (threadIdx.x == 0) A.redo[cta_id] = 0;
+  } else {
+    if (A.redo != nullptr && A.redo[cta_id] == 0) return;
+  }
   if (warp == 2) {
     tmem_alloc<L::kTmemCols>(tmem_slot);
     tmem_relinquish();
@@ -240,6 +249,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
     const uint64_t scale2 = pack_f32x2(scale, scale);
     float m_used = -INFINITY;            // reference max of the running sums (log2 domain); may lag the true max by 2^kRescaleThreshold
     uint64_t l2 = pack_f32x2(0.f, 0.f);  // row sum as two partial sums
+    float l = 0.f;                       // final row sum
 
     // p = exp2(s * scale - m_used) for one half (16 columns) of a 32-column chunk, packed to bf16; accumulates the row sum
     auto exp_half = [&](const uint32_t (&v)[32], uint32_t (&pk)[16], uint64_t negm2, const int half) {
@@ -320,14 +330,167 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       return fmax3(m0, fmax3(m2, __uint_as_float(v[23]), __uint_as_float(v[31])), m0) * scale;
     };
 
-    for (int j = 0; j < n_kv; ++j) {
-      const int valid = A.S - j * kKT;  // keys valid in this tile (>= 1)
 #ifdef TPDM_ATTN_TRACE
-      const bool tr4 = trace_on && warp == 4;
+    const bool tr4 = trace_on && warp == 4;
 #define STRACE(e) do { if (tr4 && lane == 0 && 8 * j + (e) < 2048) g_attn_trace[0][8 * j + (e)] = clock64(); } while (0)
 #else
 #define STRACE(e)
 #endif
+    if constexpr (kFast) {
+      // ------------------------------------------------------------ fast path: no maximum inside the loop
+      // The reference m_ref only has to keep exp2(s - m_ref) inside the fp32 / bf16 exponent range; it does not have to be the
+      // maximum.  It starts as the row maximum of the first key tile and is then guarded by the ROW SUM, which the loop computes
+      // anyway: at the top of every tile, l > 2^32 moves the reference up by floor(log2 l) (O and l rescaled by the same power of
+      // two; nothing of the new tile exists yet and P(j-1) V has drained by then, so no P is ever touched).  One tile can add at
+      // most a factor 2^32 per element before the next check, far inside the range.  What the guard cannot repair -- a score more
+      // than ~2^64 above everything the row has seen (l > 2^64, inf or NaN at the next check; or an argument > 127 reaching the
+      // polynomial, which would wrap instead of overflowing) -- sets this CTA's redo flag, and the exact kernel launched right
+      // behind this one recomputes the CTA with per-chunk maxima.  Per 128 keys this removes 64 FMNMX3, four votes and the
+      // serial "load chunk 0 -> maximum -> vote" prefix of every tile from the softmax warps.
+      constexpr float kSoft = 4294967296.f, kHard = 1.8446744073709552e19f, kPolyMax = 127.f;
+      uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);   // row sum as four partial sums
+      float pmax = -INFINITY;   // largest argument that went through the polynomial since the last guard
+      bool hard = false;
+      float m_ref;
+      mbar_wait(s_full, 0);
+      tc_fence_after();
+      {
+        const int valid0 = A.S < kKT ? A.S : kKT;
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < kKT / kChunk; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_tmem + c * kChunk, v);
+          tmem_wait_ld();
+          mask_chunk(c, v, valid0);
+          mx = fmaxf(mx, chunk_max(v));
+        }
+        m_ref = mx;
+      }
+      // exponentials of one 32-column chunk, packed to bf16
+      auto exp_chunk = [&](const uint32_t (&v)[32], uint32_t (&pk)[16], const uint64_t negm2) {
+        const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f), nmagic2 = pack_f32x2(-12582912.f, -12582912.f);
+        const uint64_t mone2 = pack_f32x2(-1.f, -1.f);
+        const uint64_t c0 = pack_f32x2(0.9999280572f, 0.9999280572f), c1 = pack_f32x2(0.6932609677f, 0.6932609677f),
+                       c2 = pack_f32x2(0.2426111251f, 0.2426111251f), c3 = pack_f32x2(0.0551716499f, 0.0551716499f);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x0, x1, p0, p1;
+          unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), scale2, negm2), x0, x1);
+          if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
+            pmax = fmax3(pmax, x0, x1);
+            const uint64_t xp = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+            const uint64_t t = fadd2(xp, magic2);
+            const uint64_t fr = ffma2(fadd2(t, nmagic2), mone2, xp);
+            uint64_t pp = ffma2(c3, fr, c2);
+            pp = ffma2(pp, fr, c1);
+            pp = ffma2(pp, fr, c0);
+            float t0, t1;
+            unpack_f32x2(t, t0, t1);
+            unpack_f32x2(pp, p0, p1);
+            p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+            p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+          } else {
+            p0 = exp2_approx(x0);
+            p1 = exp2_approx(x1);
+          }
+          if (i & 1) lb = fadd2(lb, pack_f32x2(p0, p1));
+          else la = fadd2(la, pack_f32x2(p0, p1));
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+      };
+      auto row_sum = [&]() {
+        float a0, a1, b0, b1;
+        unpack_f32x2(la, a0, a1);
+        unpack_f32x2(lb, b0, b1);
+        return (a0 + a1) + (b0 + b1);
+      };
+      // rare: move the reference (whole warp; rows that do not need it use alpha = 1)
+      auto renorm = [&](const int j, const float lsum) {
+        if (!(lsum <= kHard) || pmax > kPolyMax) hard = true;
+        float alpha = 1.f;
+        if (lsum > kSoft && !hard) {
+          const float m_new = m_ref + static_cast<float>((__float_as_int(lsum) >> 23) - 127);
+          alpha = exp2_approx(m_ref - m_new);
+          m_ref = m_new;
+        }
+        if (j > 0) {
+          mbar_wait(pv_done, (j - 1) & 1);   // every P V issued so far has drained: O may be touched
+          tc_fence_after();
+          rescale_o(alpha);
+        }
+        const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+        la = fmul2(la, alpha2);
+        lb = fmul2(lb, alpha2);
+        pmax = -INFINITY;
+      };
+      auto tile = [&](const int j, auto masked_tag) {
+        constexpr bool kMasked = decltype(masked_tag)::value;
+        const int valid = A.S - j * kKT;
+        STRACE(0);
+        {
+          const float lsum = row_sum();
+          if (__any_sync(0xffffffffu, !(lsum <= kSoft) || pmax > kPolyMax)) renorm(j, lsum);
+        }
+        const uint64_t negm2 = pack_f32x2(-m_ref, -m_ref);
+        mbar_wait(s_full, j & 1);
+        tc_fence_after();
+        if (warp == 4 && lane == 0) mbar_arrive(&k_empty[j % kKVStages]);   // Q K(j)^T has completed: the K stage is free
+        STRACE(1);
+        uint32_t va[32], vb[32], pk[16];
+        tmem_ld_32x32(s_tmem, va);
+        tmem_ld_32x32(s_tmem + kChunk, vb);
+        tmem_wait_ld();
+        STRACE(2);
+        if (kMasked) {
+          mask_chunk(0, va, valid);
+          mask_chunk(1, vb, valid);
+        }
+        exp_chunk(va, pk, negm2);
+        if (j > 0) {  // P is single-buffered: P(j-1) V must be done before P(j) lands
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+          if (warp == 4 && lane == 0) mbar_arrive(&v_empty[(j - 1) % kKVStages]);   // ... and its V stage is free
+        }
+        tmem_st_32x16(p_tmem, pk);
+        tmem_ld_32x32(s_tmem + 2 * kChunk, va);
+        STRACE(3);
+        exp_chunk(vb, pk, negm2);
+        tmem_st_32x16(p_tmem + 16, pk);
+        tmem_ld_32x32(s_tmem + 3 * kChunk, vb);
+        // keys [0,64) of P(j) go to the MMA warp
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[0]);
+        // all of S(j) is in registers: Q K^T of the next tile may overwrite it
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        STRACE(4);
+        if (kMasked) {
+          mask_chunk(2, va, valid);
+          mask_chunk(3, vb, valid);
+        }
+        exp_chunk(va, pk, negm2);
+        tmem_st_32x16(p_tmem + 32, pk);
+        exp_chunk(vb, pk, negm2);
+        tmem_st_32x16(p_tmem + 48, pk);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[1]);
+        STRACE(5);
+      };
+      for (int j = 0; j < n_kv - 1; ++j) tile(j, std::false_type{});
+      tile(n_kv - 1, std::true_type{});
+      l = row_sum();
+      if (!(l <= kHard) || pmax > kPolyMax) hard = true;
+      if (hard) A.redo[cta_id] = 1;
+    } else {
+    for (int j = 0; j < n_kv; ++j) {
+      const int valid = A.S - j * kKT;  // keys valid in this tile (>= 1)
       STRACE(0);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
@@ -369,6 +532,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
         const float mc = chunk_max(va);
         if (__any_sync(0xffffffffu, mc > m_used + kRescaleThreshold)) raise_reference(0, mc);
       }
+      STRACE(6);
       auto do_chunk = [&](const int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
         constexpr int kLast = kKT / kChunk - 1;
         uint32_t pk[16];
@@ -391,6 +555,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
           mbar_wait(pv_done, (j - 1) & 1);
           tc_fence_after();
           if (warp == 4 && lane == 0) mbar_arrive(&v_empty[(j - 1) % kKVStages]);   // ... and its V stage is free
+          STRACE(7);
         }
         tmem_st_32x16(p_tmem + c * 16, pk);
         if (c + 2 <= kLast) tmem_ld_32x32(s_tmem + (c + 2) * kChunk, cur);
@@ -414,7 +579,8 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
     }
     float l_lo, l_hi;
     unpack_f32x2(l2, l_lo, l_hi);
-    const float l = l_lo + l_hi;
+    l = l_lo + l_hi;
+    }
     // epilogue: O / l -> bf16, token-major
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
@@ -447,18 +613,58 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   if (warp == 2) tmem_dealloc<L::kTmemCols>(tmem_base);
 }
 
+// TPDM_ATTN_EXACT=1: only the exact kernel (per-chunk maxima), as in round 1 / early round 2 -- for A/B timing and tests
+bool exact_only() {
+  static const bool v = [] {
+    const char* e = getenv("TPDM_ATTN_EXACT");
+    return e != nullptr && e[0] == '1';
+  }();
+  return v;
+}
+
+// Redo flags of the fast kernel, one int per CTA: slices of one device buffer handed out round-robin at attn_op_init time (an op
+// keeps its slice; after a wrap two ops may share one, which is harmless on one stream: the fast kernel rewrites every flag of its
+// grid before the exact kernel behind it reads them).
+constexpr size_t kRedoCapacity = size_t(1) << 20;
+int* redo_slice(size_t n) {
+  static int* buf = nullptr;
+  static size_t cursor = 0;
+  if (n > kRedoCapacity) return nullptr;
+  if (buf == nullptr && cudaMalloc(&buf, kRedoCapacity * sizeof(int)) != cudaSuccess) {
+    buf = nullptr;
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  if (cursor + n > kRedoCapacity) cursor = 0;
+  int* p = buf + cursor;
+  cursor += n;
+  return p;
+}
+
+const int* g_last_redo = nullptr;   // slice and grid size of the last launch (tpdm_attention_redo_count)
+int g_last_redo_n = 0;
+
 template <int DP>
 int attn_launch_impl(const AttnOp& op, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    TPDM_CUDA_OK(cudaFuncSetAttribute(joint_attention_tcgen05_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TPDM_CUDA_OK(cudaFuncSetAttribute(joint_attention_tcgen05_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      AttnSmem<DP>::kTotal));
+    TPDM_CUDA_OK(cudaFuncSetAttribute(joint_attention_tcgen05_kernel<DP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       AttnSmem<DP>::kTotal));
     attr_set = true;
   }
   dim3 grid(op.q_tiles, op.H, op.Bt);
+  g_last_redo = op.redo;
+  g_last_redo_n = op.q_tiles * op.H * op.Bt;
   const double q_rows = op.q_tiles * kQT < op.S ? op.q_tiles * kQT : op.S;
   prof_begin(1, 4.0 * op.Bt * op.H * q_rows * op.S * op.head_dim, stream);
-  TPDM_CUDA_OK(launch_pdl(joint_attention_tcgen05_kernel<DP>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
+  if (op.redo != nullptr) {
+    // fast kernel, then the exact kernel over the same grid: its CTAs return at once unless the fast one flagged them
+    TPDM_CUDA_OK(launch_pdl(joint_attention_tcgen05_kernel<DP, true>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
+    count_launch();
+  }
+  TPDM_CUDA_OK(launch_pdl(joint_attention_tcgen05_kernel<DP, false>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
   prof_end(stream);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
@@ -480,6 +686,7 @@ int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int 
   op->q_tiles = (S + kQT - 1) / kQT;
   op->scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
   op->out = reinterpret_cast<__nv_bfloat16*>(out);
+  op->redo = redo_slice(static_cast<size_t>(op->q_tiles) * H * Bt);
   const uint64_t row = static_cast<uint64_t>(3) * H * dp;  // elements per token in the fused qkv buffer
   uint64_t dims[4] = {static_cast<uint64_t>(dp), static_cast<uint64_t>(H), static_cast<uint64_t>(S), static_cast<uint64_t>(Bt)};
   uint64_t strides[3] = {static_cast<uint64_t>(dp) * 2, row * 2, row * S * 2};
@@ -489,6 +696,22 @@ int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int 
   TPDM_TRY(encode_tmap_bf16(&op->tmK, base + static_cast<size_t>(H) * dp, 4, dims, strides, box));
   TPDM_TRY(encode_tmap_bf16(&op->tmV, base + static_cast<size_t>(2) * H * dp, 4, dims, strides, box));
   return 0;
+}
+
+int attn_redo_count() {
+  if (g_last_redo == nullptr) return -1;
+  static int* host = nullptr;
+  static int host_n = 0;
+  if (host_n < g_last_redo_n) {
+    free(host);
+    host = static_cast<int*>(malloc(sizeof(int) * g_last_redo_n));
+    host_n = g_last_redo_n;
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpy(host, g_last_redo, sizeof(int) * g_last_redo_n, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  int n = 0;
+  for (int i = 0; i < g_last_redo_n; ++i) n += host[i] != 0;
+  return n;
 }
 
 #ifdef TPDM_ATTN_TRACE
@@ -502,6 +725,7 @@ int attn_launch(const AttnOp* op_in, cudaStream_t stream) {
   op_copy.skip = skip_flag();
   op_copy.bmask = batch_mask();
   op_copy.bslots = batch_mask_slots();
+  if (exact_only()) op_copy.redo = nullptr;
   const AttnOp* op = &op_copy;
   return op->dp == 64 ? attn_launch_impl<64>(*op, stream) : attn_launch_impl<128>(*op, stream);
 }

@@ -22,7 +22,9 @@ lib.tpdm_attn_trace_read.argtypes = [C.POINTER(C.c_longlong), C.c_int]
 assert lib.tpdm_attn_trace_read(buf, 3 * 2048) == 0
 sm, qk, pv = ([buf[r * 2048 + i] for i in range(2048)] for r in range(3))
 n_kv = (S + 127) // 128
-names = ["wait s_full", "ld chunk 0", "max + chunk 0 (pv_done wait, st)", "chunks 1-2 (+ p_full half 0)", "chunk 3 + p_full"]
+names = (["guard + wait s_full", "ld chunks 0-1", "chunk 0 (pv_done wait, st)", "chunk 1 + p_full[0] + s_free", "chunks 2-3 + p_full[1]"]
+         if os.environ.get("TPDM_ATTN_EXACT") != "1" else
+         ["wait s_full", "ld chunk 0", "max + chunk 0 (pv_done wait, st)", "chunks 1-2 (+ p_full half 0)", "chunk 3 + p_full"])
 print("softmax warp 4 of one CTA, cycles per phase of a 128-key tile (period = top(j+1) - top(j))")
 tot = [0.0] * 6
 cnt = 0

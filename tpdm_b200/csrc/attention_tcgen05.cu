@@ -86,39 +86,30 @@ struct AttnSmem {
   static constexpr uint32_t kOCol = 192;   // O: DP columns
 };
 
-template <int DP, bool kFast>
-__global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attention_tcgen05_kernel(const __grid_constant__ AttnOp A) {
-  using L = AttnSmem<DP>;
-  pdl_launch_dependents();
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;                 // [kKVStages]
-  uint64_t* v_full = k_full + kKVStages;       // [kKVStages]
-  uint64_t* k_empty = v_full + kKVStages;      // [kKVStages]
-  uint64_t* v_empty = k_empty + kKVStages;     // [kKVStages]
-  uint64_t* s_full = v_empty + kKVStages;      // MMA -> softmax : S(j) written
-  uint64_t* s_free = s_full + 1;               // softmax -> MMA : S(j) is in registers
-  uint64_t* p_full = s_free + 1;               // [2] softmax -> MMA : keys [0,64) / [64,128) of P(j) written (and O rescaled if needed)
-  uint64_t* pv_done = p_full + 2;              // MMA -> softmax : P(j) V accumulated (P may be overwritten, O may be touched)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qt * kQT;
-  const int n_kv = (A.S + kKT - 1) / kKT;
-#ifdef TPDM_ATTN_TRACE
-  const bool trace_on = blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 0;
-#endif
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&A.tmQ);
-    tma_prefetch_desc(&A.tmK);
-    tma_prefetch_desc(&A.tmV);
+// mbarriers of one CTA, in the order they are laid out behind the tiles
+template <int DP>
+struct AttnBars {
+  uint64_t *q_full, *k_full, *v_full, *k_empty, *v_empty, *s_full, *s_free, *p_full, *pv_done;
+  uint32_t* tmem_slot;
+  __device__ explicit AttnBars(uint8_t* smem) {
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem<DP>::kBarOff);
+    q_full = bars + 0;
+    k_full = bars + 1;                 // [kKVStages]
+    v_full = k_full + kKVStages;       // [kKVStages]
+    k_empty = v_full + kKVStages;      // [kKVStages]
+    v_empty = k_empty + kKVStages;     // [kKVStages]
+    s_full = v_empty + kKVStages;      // MMA -> softmax : S(j) written
+    s_free = s_full + 1;               // softmax -> MMA : S(j) is in registers
+    p_full = s_free + 1;               // [2] softmax -> MMA : keys [0,64) / [64,128) of P(j) written (and O rescaled if needed)
+    pv_done = p_full + 2;              // MMA -> softmax : P(j) V accumulated (P may be overwritten, O may be touched)
+    tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
   }
-  if (warp == 1 && lane == 0) {
+  static constexpr int kCount = 1 + 4 * kKVStages + 5;
+  // one thread; `again`: the barriers carry the phases of a finished tile (persistent exact kernel) and are invalidated first
+  __device__ void init(bool again) const {
+    if (again) {
+      for (int i = 0; i < kCount; ++i) mbar_inval(q_full + i);
+    }
     mbar_init(q_full, 1);
     for (int i = 0; i < kKVStages; ++i) {
       mbar_init(&k_full[i], 1);
@@ -133,24 +124,30 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  pdl_wait();
-  if (A.skip != nullptr && *A.skip != 0) return;
-  if (A.bmask != nullptr && A.bmask[blockIdx.z % A.bslots] == 0) return;  // emptied queue slot
-  // fast kernel: this CTA's "redo" flag starts at 0; exact kernel launched behind it: only flagged CTAs run (see attn_launch)
-  const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-  if constexpr (kFast) {
-    if (threadIdx.x == 0) A.redo[cta_id] = 0;
-  } else {
-    if (A.redo != nullptr && A.redo[cta_id] == 0) return;
-  }
-  if (warp == 2) {
-    tmem_alloc<L::kTmemCols>(tmem_slot);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+};
+
+__device__ __forceinline__ uint8_t* attn_smem_base() {
+  extern __shared__ uint8_t smem_raw[];
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+}
+
+// One 128-row query tile (qt) of one (batch b, head h): the whole CTA, from initialised mbarriers and an allocated TMEM block to
+// the stores of O.  kFast selects the guarded softmax without per-chunk maxima (redo_smem: set when the tile must be recomputed exactly).
+template <int DP, bool kFast>
+__device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const int qt, const int h, const int b, int* redo_smem) {
+  using L = AttnSmem<DP>;
+  const AttnBars<DP> B(smem);
+  uint64_t *const q_full = B.q_full, *const k_full = B.k_full, *const v_full = B.v_full, *const k_empty = B.k_empty,
+                 *const v_empty = B.v_empty, *const s_full = B.s_full, *const s_free = B.s_free, *const p_full = B.p_full,
+                 *const pv_done = B.pv_done;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = qt * kQT;
+  const int n_kv = (A.S + kKT - 1) / kKT;
+#ifdef TPDM_ATTN_TRACE
+  const bool trace_on = kFast == (TPDM_ATTN_TRACE != 2) && qt == 5 && h == 3 && b == 0;
+#endif
+  const uint32_t tmem_base = *B.tmem_slot;
 
   if (warp < 4) {
   if (warp == 0) {
@@ -344,8 +341,8 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       // two; nothing of the new tile exists yet and P(j-1) V has drained by then, so no P is ever touched).  One tile can add at
       // most a factor 2^32 per element before the next check, far inside the range.  What the guard cannot repair -- a score more
       // than ~2^64 above everything the row has seen (l > 2^64, inf or NaN at the next check; or an argument > 127 reaching the
-      // polynomial, which would wrap instead of overflowing) -- sets this CTA's redo flag, and the exact kernel launched right
-      // behind this one recomputes the CTA with per-chunk maxima.  Per 128 keys this removes 64 FMNMX3, four votes and the
+      // polynomial, which would wrap instead of overflowing) -- sets this CTA's redo flag, and the CTA then runs its tile a second time with the
+      // exact softmax (per-chunk maxima, the `else` branch below) before it exits.  Per 128 keys this removes 64 FMNMX3, four votes and the
       // serial "load chunk 0 -> maximum -> vote" prefix of every tile from the softmax warps.
       constexpr float kSoft = 4294967296.f, kHard = 1.8446744073709552e19f, kPolyMax = 127.f;
       uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);   // row sum as four partial sums
@@ -487,7 +484,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
       tile(n_kv - 1, std::true_type{});
       l = row_sum();
       if (!(l <= kHard) || pmax > kPolyMax) hard = true;
-      if (hard) A.redo[cta_id] = 1;
+      if (hard) *redo_smem = 1;
     } else {
     for (int j = 0; j < n_kv; ++j) {
       const int valid = A.S - j * kKT;  // keys valid in this tile (>= 1)
@@ -610,7 +607,79 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<L::kTmemCols>(tmem_base);
+}
+
+// Fast kernel: one CTA per (query tile, head, batch entry).  A CTA whose softmax warps met scores the row-sum guard cannot keep in
+// range (see attn_cta) runs its tile a second time with the exact softmax (per-chunk maxima) before it exits -- same TMEM block,
+// mbarriers re-initialised.  On ordinary activations no CTA does.
+template <int DP>
+__global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attention_fast_kernel(const __grid_constant__ AttnOp A) {
+  using L = AttnSmem<DP>;
+  pdl_launch_dependents();
+  uint8_t* smem = attn_smem_base();
+  const AttnBars<DP> B(smem);
+  __shared__ int redo_smem;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&A.tmQ);
+    tma_prefetch_desc(&A.tmK);
+    tma_prefetch_desc(&A.tmV);
+  }
+  if (warp == 1 && lane == 0) B.init(false);
+  if (threadIdx.x == 0) redo_smem = 0;
+  pdl_wait();
+  const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const bool idle = (A.skip != nullptr && *A.skip != 0) || (A.bmask != nullptr && A.bmask[blockIdx.z % A.bslots] == 0);
+  if (idle) {   // a speculative step after the trajectory's end, or an emptied queue slot
+    if (A.redo != nullptr && threadIdx.x == 0) A.redo[cta_id] = 0;
+    return;
+  }
+  if (warp == 2) {
+    tmem_alloc<L::kTmemCols>(B.tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  attn_cta<DP, true>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, &redo_smem);   // ends with a CTA-wide barrier
+  const int redo = redo_smem;
+  if (redo != 0) {
+    if (warp == 1 && lane == 0) B.init(true);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    attn_cta<DP, false>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, nullptr);
+  }
+  if (A.redo != nullptr && threadIdx.x == 0) A.redo[cta_id] = redo;   // diagnostic: tpdm_attention_redo_count
+  if (warp == 2) tmem_dealloc<L::kTmemCols>(*B.tmem_slot);
+}
+
+// Exact kernel alone (TPDM_ATTN_EXACT=1): per-chunk maxima from the first tile on, as in round 1 / early round 2.
+template <int DP>
+__global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attention_exact_kernel(const __grid_constant__ AttnOp A) {
+  using L = AttnSmem<DP>;
+  pdl_launch_dependents();
+  uint8_t* smem = attn_smem_base();
+  const AttnBars<DP> B(smem);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&A.tmQ);
+    tma_prefetch_desc(&A.tmK);
+    tma_prefetch_desc(&A.tmV);
+  }
+  if (warp == 1 && lane == 0) B.init(false);
+  pdl_wait();
+  if (A.skip != nullptr && *A.skip != 0) return;
+  if (A.bmask != nullptr && A.bmask[blockIdx.z % A.bslots] == 0) return;  // emptied queue slot
+  if (warp == 2) {
+    tmem_alloc<L::kTmemCols>(B.tmem_slot);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  attn_cta<DP, false>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, nullptr);
+  if (warp == 2) tmem_dealloc<L::kTmemCols>(*B.tmem_slot);
 }
 
 // TPDM_ATTN_EXACT=1: only the exact kernel (per-chunk maxima), as in round 1 / early round 2 -- for A/B timing and tests
@@ -648,23 +717,19 @@ template <int DP>
 int attn_launch_impl(const AttnOp& op, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    TPDM_CUDA_OK(cudaFuncSetAttribute(joint_attention_tcgen05_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      AttnSmem<DP>::kTotal));
-    TPDM_CUDA_OK(cudaFuncSetAttribute(joint_attention_tcgen05_kernel<DP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      AttnSmem<DP>::kTotal));
+    TPDM_CUDA_OK(cudaFuncSetAttribute(joint_attention_fast_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<DP>::kTotal));
+    TPDM_CUDA_OK(cudaFuncSetAttribute(joint_attention_exact_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem<DP>::kTotal));
     attr_set = true;
   }
   dim3 grid(op.q_tiles, op.H, op.Bt);
-  g_last_redo = op.redo;
+  g_last_redo = exact_only() ? nullptr : op.redo;
   g_last_redo_n = op.q_tiles * op.H * op.Bt;
   const double q_rows = op.q_tiles * kQT < op.S ? op.q_tiles * kQT : op.S;
   prof_begin(1, 4.0 * op.Bt * op.H * q_rows * op.S * op.head_dim, stream);
-  if (op.redo != nullptr) {
-    // fast kernel, then the exact kernel over the same grid: its CTAs return at once unless the fast one flagged them
-    TPDM_CUDA_OK(launch_pdl(joint_attention_tcgen05_kernel<DP, true>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
-    count_launch();
-  }
-  TPDM_CUDA_OK(launch_pdl(joint_attention_tcgen05_kernel<DP, false>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
+  if (exact_only())
+    TPDM_CUDA_OK(launch_pdl(joint_attention_exact_kernel<DP>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
+  else
+    TPDM_CUDA_OK(launch_pdl(joint_attention_fast_kernel<DP>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
   prof_end(stream);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());
@@ -725,7 +790,6 @@ int attn_launch(const AttnOp* op_in, cudaStream_t stream) {
   op_copy.skip = skip_flag();
   op_copy.bmask = batch_mask();
   op_copy.bslots = batch_mask_slots();
-  if (exact_only()) op_copy.redo = nullptr;
   const AttnOp* op = &op_copy;
   return op->dp == 64 ? attn_launch_impl<64>(*op, stream) : attn_launch_impl<128>(*op, stream);
 }

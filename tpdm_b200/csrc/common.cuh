@@ -30,6 +30,9 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
 // Programmatic dependent launch (host side: launch_pdl in host.h).  A kernel lets the next grid in the stream start
 // being scheduled as soon as every CTA of this one has been launched (launch_dependents at the very top), and it must
 // itself pass pdl_wait() -- which returns once ALL earlier grids have completed and their stores are visible --

@@ -57,3 +57,14 @@ for role, name, arr in ((1, "QK issuer", qk), (2, "PV issuer", pv)):
     print(f"{name}: mean wait {w / c:.1f} cycles, issue+commit {s_ / c:.1f} cycles per 128-key tile")
 lag_s = [sm[8 * j + 1] - qk[4 * j + 2] for j in range(4, n_kv - 2) if sm[8 * j + 1] and qk[4 * j + 2]]
 print(f"S(j) issued -> softmax(j) past its wait: mean {sum(lag_s) / len(lag_s):.0f} cycles (min {min(lag_s)}, max {max(lag_s)})")
+
+cbuf = (C.c_longlong * 32)()
+if hasattr(lib, "tpdm_attn_cta_trace_read") and lib.tpdm_attn_cta_trace_read(cbuf) == 0:
+    for c, name in ((0, "CTA (qt 5, head 3, batch 0) -- first wave"), (1, "CTA (qt 7, head 20, batch 1) -- late wave")):
+        t = [cbuf[16 * c + i] for i in range(9)]
+        if not t[6]:
+            continue
+        cyc, ns = t[6] - t[0], t[8] - t[7]
+        print(f"{name}: {cyc} cycles = {ns} ns ({cyc / max(ns, 1):.3f} GHz): entry->pdl_wait {t[1] - t[0]}, TMEM alloc + sync {t[2] - t[1]}, "
+              f"first score tile + its maximum {t[3] - t[2]}, {n_kv} key tiles {t[4] - t[3]} ({(t[4] - t[3]) / n_kv:.0f} each), "
+              f"last P V + O store {t[5] - t[4]}, exit {t[6] - t[5]}")

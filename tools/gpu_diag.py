@@ -264,6 +264,8 @@ if __name__ == "__main__":
             ms = timeit(lambda: lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, 64, d, 0, None), 20)
             print(f"{'tpdm joint_attention':26s} Bt={Bt} H={H} S={S} d={d}: {ms*1e3:8.1f} us  {flops/ms/1e9:7.1f} TFLOP/s", flush=True)
             del q, k, v, qkv, out
+    if which == "attn_time":   # the SD3-medium 1024^2 block shape only, timed (kernel experiments: TPDM_B200_LIB=... variants)
+        attn_case(2, 4429, 24, 64, 0, True)
     if which == "attn_big":
         attn_case(2, 4429, 24, 64)
         attn_case(2, 4429, 24, 64)

@@ -60,6 +60,14 @@ constexpr float kRescaleThreshold = 32.0f;  // log2 units
 #define TPDM_POLY_EVERY 4
 #endif
 constexpr int kPolyEvery = TPDM_POLY_EVERY;
+// Fast path experiments (profiles/r02_attention_experiments.txt): hand P(j) to the MMA warp once per tile instead of in two halves;
+// evaluate the row-sum guard on the sums as they stood one chunk earlier (off the MUFU drain at the top of a tile).
+#ifndef TPDM_ATTN_ONE_HANDOVER
+#define TPDM_ATTN_ONE_HANDOVER 1
+#endif
+#ifndef TPDM_ATTN_STALE_GUARD
+#define TPDM_ATTN_STALE_GUARD 1
+#endif
 // -DTPDM_ATTN_TRACE: clock64() time stamps of one CTA's softmax warp 4 (role 0, 8 slots per key tile) and of the two MMA-issuing
 // warps (roles 1 and 2, 4 slots per key tile), read back with tpdm_attn_trace_read (tools/attn_trace.py).  Diagnostic builds only.
 #ifdef TPDM_ATTN_TRACE
@@ -68,8 +76,16 @@ __device__ long long g_attn_trace[3][2048];
   do {                                                                                          \
     if (trace_on && lane == 0 && (idx) < 2048) g_attn_trace[role][idx] = clock64();             \
   } while (0)
+// CTA-level stamps of two CTAs (an early and a late one): [0] kernel entry, [1] past pdl_wait, [2] TMEM allocated, [3] first score
+// tile ready, [4] last tile's P handed over, [5] O stored, [6] exit; [7] = %globaltimer at entry, [8] at exit
+__device__ long long g_cta_trace[2][16];
+#define CTRACE(idx)                                                                             \
+  do {                                                                                          \
+    if (ctr >= 0 && threadIdx.x == 128) g_cta_trace[ctr][idx] = clock64();                      \
+  } while (0)
 #else
 #define ATRACE(role, idx)
+#define CTRACE(idx)
 #endif
 
 template <int DP>
@@ -84,12 +100,14 @@ struct AttnSmem {
   static constexpr uint32_t kSCol = 0;     // S: 128 fp32 columns
   static constexpr uint32_t kPCol = 128;   // P: 64 columns (128 keys, packed bf16)
   static constexpr uint32_t kOCol = 192;   // O: DP columns
+  // fast path: three regions of 64 columns instead of S + P (see the Q K^T issuer)
+  static constexpr uint32_t kR0Col = 0, kR1Col = 64, kR2Col = 128;
 };
 
 // mbarriers of one CTA, in the order they are laid out behind the tiles
 template <int DP>
 struct AttnBars {
-  uint64_t *q_full, *k_full, *v_full, *k_empty, *v_empty, *s_full, *s_free, *p_full, *pv_done;
+  uint64_t *q_full, *k_full, *v_full, *k_empty, *v_empty, *s_full, *s_free, *p_full, *pv_done, *sa_full;
   uint32_t* tmem_slot;
   __device__ explicit AttnBars(uint8_t* smem) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AttnSmem<DP>::kBarOff);
@@ -102,9 +120,10 @@ struct AttnBars {
     s_free = s_full + 1;               // softmax -> MMA : S(j) is in registers
     p_full = s_free + 1;               // [2] softmax -> MMA : keys [0,64) / [64,128) of P(j) written (and O rescaled if needed)
     pv_done = p_full + 2;              // MMA -> softmax : P(j) V accumulated (P may be overwritten, O may be touched)
-    tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 1);
+    sa_full = pv_done + 1;             // [2] fast path: MMA -> softmax : keys [0,64) of S(j) written (s_full / s_free then stand for keys [64,128))
+    tmem_slot = reinterpret_cast<uint32_t*>(sa_full + 2);
   }
-  static constexpr int kCount = 1 + 4 * kKVStages + 5;
+  static constexpr int kCount = 1 + 4 * kKVStages + 5 + 2;
   // one thread; `again`: the barriers carry the phases of a finished tile (persistent exact kernel) and are invalidated first
   __device__ void init(bool again) const {
     if (again) {
@@ -122,6 +141,8 @@ struct AttnBars {
     mbar_init(&p_full[0], 4);
     mbar_init(&p_full[1], 4);
     mbar_init(pv_done, 1);
+    mbar_init(&sa_full[0], 1);
+    mbar_init(&sa_full[1], 1);
     fence_barrier_init();
   }
 };
@@ -139,7 +160,7 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
   const AttnBars<DP> B(smem);
   uint64_t *const q_full = B.q_full, *const k_full = B.k_full, *const v_full = B.v_full, *const k_empty = B.k_empty,
                  *const v_empty = B.v_empty, *const s_full = B.s_full, *const s_free = B.s_free, *const p_full = B.p_full,
-                 *const pv_done = B.pv_done;
+                 *const pv_done = B.pv_done, *const sa_full = B.sa_full;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = qt * kQT;
@@ -177,9 +198,49 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer: S(j) = Q K(j)^T
-    constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, false);
     const uint32_t q_base = smem_u32(smem + L::kQOff);
     mbar_wait(q_full, 0);
+    if constexpr (kFast) {
+      // Fast path: S(j) is produced as two halves of 64 keys (N = 64 MMAs).  Keys [64,128) always land in TMEM region R1; keys
+      // [0,64) alternate between R0 (even j) and R2 (odd j), and P(j) is later written OVER that region (its S values are in
+      // registers by then).  With three S regions and a double-buffered P in 192 columns, the first half of S(j) is issued as soon
+      // as P(j-2) V has drained -- a whole tile ahead of its use -- and the second half as soon as the softmax warps hold the
+      // second half of S(j-1) in registers: the softmax warps never wait for P V, and practically never for Q K^T.
+      static_assert(kKVStages == 2, "the V stage released here is that of tile j - 2");
+      constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT / 2, false);
+      for (int j = 0; j < n_kv; ++j) {
+        const int stage = j % kKVStages;
+        ATRACE(1, 4 * j);
+        if (j >= 2) {
+          mbar_wait_backoff(pv_done, j & 1);                    // P(j-2) V has drained: its TMEM region and its V stage are free
+          if (lane == 0) mbar_arrive(&v_empty[stage]);
+          __syncwarp();
+        }
+        mbar_wait(&k_full[stage], (j / kKVStages) & 1);
+        tc_fence_after();
+        ATRACE(1, 4 * j + 1);
+        const uint32_t k_base = smem_u32(smem + L::kKOff + stage * L::kTile);
+        const uint64_t qdesc0 = make_smem_desc_sw128(q_base, 16, 1024), kdesc0 = make_smem_desc_sw128(k_base, 16, 1024);
+#pragma unroll
+        for (int ks = 0; ks < DP / 16; ++ks) {
+          const uint32_t off = ((ks / 4) * (kQT * 128) + (ks % 4) * 32) >> 4;   // the start-address field counts 16-byte units
+          umma_ss_elect(tmem_base + ((j & 1) ? L::kR2Col : L::kR0Col), qdesc0 + off, kdesc0 + off, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        umma_commit_elect(&sa_full[j & 1]);
+        ATRACE(1, 4 * j + 2);
+        if (j >= 1) mbar_wait_backoff(s_free, (j - 1) & 1);     // the softmax warps hold keys [64,128) of S(j-1) in registers
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < DP / 16; ++ks) {
+          const uint32_t off = ((ks / 4) * (kQT * 128) + (ks % 4) * 32) >> 4;
+          umma_ss_elect(tmem_base + L::kR1Col, qdesc0 + off, kdesc0 + off + ((kKT / 2) * 128 >> 4), idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        umma_commit_elect(s_full);   // the K stage is handed back to the TMA warp by the softmax warp that observes s_full
+        ATRACE(1, 4 * j + 3);
+        __syncwarp();
+      }
+    } else {
+    constexpr uint32_t idesc_qk = make_idesc_bf16(kQT, kKT, false);
     for (int j = 0; j < n_kv; ++j) {
       const int stage = j % kKVStages;
       ATRACE(1, 4 * j);
@@ -201,6 +262,7 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
       }
       ATRACE(1, 4 * j + 2);
       __syncwarp();
+    }
     }
   } else if (warp == 3) {
     // ---------------------------------------------------------------- MMA issuer: O += P(j) V(j)
@@ -225,7 +287,9 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
 #pragma unroll
           for (int k4 = 0; k4 < kKT / 32; ++k4) {
             const int ks = half * (kKT / 32) + k4;
-            umma_ts_elect(tmem_base + L::kOCol, tmem_base + L::kPCol + ks * 8, vdesc0 + ks * (2048 >> 4), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+            // fast path: P(j) lies over the region that held keys [0,64) of S(j)
+            const uint32_t p_col = kFast ? ((j & 1) ? L::kR2Col : L::kR0Col) : L::kPCol;
+            umma_ts_elect(tmem_base + L::kOCol, tmem_base + p_col + ks * 8, vdesc0 + ks * (2048 >> 4), idesc_pv, (j | ks) != 0 ? 1u : 0u);
           }
           if (half == 1) umma_commit_elect(pv_done);   // the V stage is released by the softmax warp that observes pv_done
         }
@@ -347,8 +411,9 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
       constexpr float kSoft = 4294967296.f, kHard = 1.8446744073709552e19f, kPolyMax = 127.f;
       uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);   // row sum as four partial sums
       float pmax = -INFINITY;   // largest argument that went through the polynomial since the last guard
-      bool hard = false;
+      bool hard = false, suspect = false;
       float m_ref;
+      mbar_wait(&sa_full[0], 0);
       mbar_wait(s_full, 0);
       tc_fence_after();
       {
@@ -357,13 +422,19 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
 #pragma unroll 1
         for (int c = 0; c < kKT / kChunk; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32(s_tmem + c * kChunk, v);
+          tmem_ld_32x32(s_tmem + c * kChunk, v);   // S(0): regions R0 and R1 are adjacent
           tmem_wait_ld();
           mask_chunk(c, v, valid0);
           mx = fmaxf(mx, chunk_max(v));
         }
         m_ref = mx;
       }
+#ifdef TPDM_ATTN_TRACE
+      if (threadIdx.x == 128) {
+        const int ctr2 = (qt == 5 && h == 3 && b == 0) ? 0 : (qt == 7 && h == 20 && b == 1) ? 1 : -1;
+        if (ctr2 >= 0) g_cta_trace[ctr2][3] = clock64();
+      }
+#endif
       // exponentials of one 32-column chunk, packed to bf16
       auto exp_chunk = [&](const uint32_t (&v)[32], uint32_t (&pk)[16], const uint64_t negm2) {
         const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f), nmagic2 = pack_f32x2(-12582912.f, -12582912.f);
@@ -420,23 +491,30 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
         la = fmul2(la, alpha2);
         lb = fmul2(lb, alpha2);
         pmax = -INFINITY;
+        suspect = false;
       };
       auto tile = [&](const int j, auto masked_tag) {
         constexpr bool kMasked = decltype(masked_tag)::value;
         const int valid = A.S - j * kKT;
+        // keys [0,64) of S(j), and later all of P(j), live in R0 (even j) or R2 (odd j); keys [64,128) of S(j) in R1
+        const uint32_t ra_tmem = tmem_base + lane_off + ((j & 1) ? L::kR2Col : L::kR0Col);
+        const uint32_t rb_tmem = tmem_base + lane_off + L::kR1Col;
         STRACE(0);
-        {
+        if (TPDM_ATTN_STALE_GUARD) {
+          // `suspect` was evaluated before the last chunk of the previous tile: the vote does not wait for that chunk's exponentials
+          // to drain.  What the last chunk added is seen one tile later (renorm itself works on the current sums).
+          if (__any_sync(0xffffffffu, suspect)) renorm(j, row_sum());
+        } else {
           const float lsum = row_sum();
           if (__any_sync(0xffffffffu, !(lsum <= kSoft) || pmax > kPolyMax)) renorm(j, lsum);
         }
         const uint64_t negm2 = pack_f32x2(-m_ref, -m_ref);
-        mbar_wait(s_full, j & 1);
+        mbar_wait(&sa_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
-        if (warp == 4 && lane == 0) mbar_arrive(&k_empty[j % kKVStages]);   // Q K(j)^T has completed: the K stage is free
         STRACE(1);
         uint32_t va[32], vb[32], pk[16];
-        tmem_ld_32x32(s_tmem, va);
-        tmem_ld_32x32(s_tmem + kChunk, vb);
+        tmem_ld_32x32(ra_tmem, va);
+        tmem_ld_32x32(ra_tmem + kChunk, vb);
         tmem_wait_ld();
         STRACE(2);
         if (kMasked) {
@@ -444,23 +522,23 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
           mask_chunk(1, vb, valid);
         }
         exp_chunk(va, pk, negm2);
-        if (j > 0) {  // P is single-buffered: P(j-1) V must be done before P(j) lands
-          mbar_wait(pv_done, (j - 1) & 1);
-          tc_fence_after();
-          if (warp == 4 && lane == 0) mbar_arrive(&v_empty[(j - 1) % kKVStages]);   // ... and its V stage is free
-        }
-        tmem_st_32x16(p_tmem, pk);
-        tmem_ld_32x32(s_tmem + 2 * kChunk, va);
+        tmem_st_32x16(ra_tmem, pk);            // over keys [0,16) of S(j), which are in registers
+        mbar_wait(s_full, j & 1);              // keys [64,128) of S(j): issued half a tile ago
+        tc_fence_after();
+        if (warp == 4 && lane == 0) mbar_arrive(&k_empty[j % kKVStages]);   // both halves of Q K(j)^T have completed: the K stage is free
+        tmem_ld_32x32(rb_tmem, va);
         STRACE(3);
         exp_chunk(vb, pk, negm2);
-        tmem_st_32x16(p_tmem + 16, pk);
-        tmem_ld_32x32(s_tmem + 3 * kChunk, vb);
+        tmem_st_32x16(ra_tmem + 16, pk);
+        tmem_ld_32x32(rb_tmem + kChunk, vb);
         // keys [0,64) of P(j) go to the MMA warp
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[0]);
-        // all of S(j) is in registers: Q K^T of the next tile may overwrite it
+        if (!TPDM_ATTN_ONE_HANDOVER) {
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[0]);
+        }
+        // the second half of S(j) is in registers: the second half of Q K^T of the next tile may overwrite R1
         tmem_wait_ld();
         tc_fence_before();
         __syncwarp();
@@ -471,17 +549,27 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
           mask_chunk(3, vb, valid);
         }
         exp_chunk(va, pk, negm2);
-        tmem_st_32x16(p_tmem + 32, pk);
+        tmem_st_32x16(ra_tmem + 32, pk);
+        if (TPDM_ATTN_STALE_GUARD) suspect = !(row_sum() <= kSoft) || pmax > kPolyMax;
         exp_chunk(vb, pk, negm2);
-        tmem_st_32x16(p_tmem + 48, pk);
+        tmem_st_32x16(ra_tmem + 48, pk);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[1]);
+        if (lane == 0) {
+          if (TPDM_ATTN_ONE_HANDOVER) mbar_arrive(&p_full[0]);
+          mbar_arrive(&p_full[1]);
+        }
         STRACE(5);
       };
       for (int j = 0; j < n_kv - 1; ++j) tile(j, std::false_type{});
       tile(n_kv - 1, std::true_type{});
+#ifdef TPDM_ATTN_TRACE
+      if (threadIdx.x == 128) {
+        const int ctr2 = (qt == 5 && h == 3 && b == 0) ? 0 : (qt == 7 && h == 20 && b == 1) ? 1 : -1;
+        if (ctr2 >= 0) g_cta_trace[ctr2][4] = clock64();
+      }
+#endif
       l = row_sum();
       if (!(l <= kHard) || pmax > kPolyMax) hard = true;
       if (hard) *redo_smem = 1;
@@ -620,6 +708,15 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   const AttnBars<DP> B(smem);
   __shared__ int redo_smem;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef TPDM_ATTN_TRACE
+  const int ctr = (blockIdx.x == 5 && blockIdx.y == 3 && blockIdx.z == 0) ? 0 : (blockIdx.x == 7 && blockIdx.y == 20 && blockIdx.z == 1) ? 1 : -1;
+  if (ctr >= 0 && threadIdx.x == 128) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cta_trace[ctr][7] = t;
+  }
+#endif
+  CTRACE(0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&A.tmQ);
     tma_prefetch_desc(&A.tmK);
@@ -628,6 +725,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   if (warp == 1 && lane == 0) B.init(false);
   if (threadIdx.x == 0) redo_smem = 0;
   pdl_wait();
+  CTRACE(1);
   const int cta_id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const bool idle = (A.skip != nullptr && *A.skip != 0) || (A.bmask != nullptr && A.bmask[blockIdx.z % A.bslots] == 0);
   if (idle) {   // a speculative step after the trajectory's end, or an emptied queue slot
@@ -641,7 +739,9 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  CTRACE(2);
   attn_cta<DP, true>(A, smem, blockIdx.x, blockIdx.y, blockIdx.z, &redo_smem);   // ends with a CTA-wide barrier
+  CTRACE(5);
   const int redo = redo_smem;
   if (redo != 0) {
     if (warp == 1 && lane == 0) B.init(true);
@@ -652,6 +752,14 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   }
   if (A.redo != nullptr && threadIdx.x == 0) A.redo[cta_id] = redo;   // diagnostic: tpdm_attention_redo_count
   if (warp == 2) tmem_dealloc<L::kTmemCols>(*B.tmem_slot);
+#ifdef TPDM_ATTN_TRACE
+  CTRACE(6);
+  if (ctr >= 0 && threadIdx.x == 128) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cta_trace[ctr][8] = t;
+  }
+#endif
 }
 
 // Exact kernel alone (TPDM_ATTN_EXACT=1): per-chunk maxima from the first tile on, as in round 1 / early round 2.
@@ -780,6 +888,9 @@ int attn_redo_count() {
 }
 
 #ifdef TPDM_ATTN_TRACE
+extern "C" int tpdm_attn_cta_trace_read(long long* host) {
+  return cudaMemcpyFromSymbol(host, g_cta_trace, sizeof(long long) * 32) == cudaSuccess ? 0 : -1;
+}
 extern "C" int tpdm_attn_trace_read(long long* host, int n) {
   return cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(long long) * (n < 3 * 2048 ? n : 3 * 2048)) == cudaSuccess ? 0 : -1;
 }

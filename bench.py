@@ -109,10 +109,10 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of round 2 (profiles/r02_attention_ncu.txt;
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture of round 2 (profiles/r02_attention_fast_ncu.txt;
 # profiles/r02_gemm2_vs_cublas_ncu.txt: mean of the four per-block shapes 71.1 / 105.5 / 272.2 / 95.7 MB).  Algorithmic bytes per launch:
 # attention 2 x 24 x 4429 x 64 x 2 B x 4 (Q, K, V, O) = 109 MB; GEMMs 71 / 136 / 237 / 128 MB.
-NCU_DRAM_BYTES_PER_LAUNCH = {"gemm_bf16_tcgen05": 136.1e6, "joint_attention_tcgen05": 91.5e6}
+NCU_DRAM_BYTES_PER_LAUNCH = {"gemm_bf16_tcgen05": 136.1e6, "joint_attention_tcgen05": 91.9e6}
 
 
 def mmdit_flops_1024() -> float:

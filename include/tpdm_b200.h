@@ -357,6 +357,8 @@ int tpdm_joint_attention(const void* qkv, void* out, int Bt, int S, int H, int d
  * exact kernel (scores more than ~2^64 above everything their row had seen before); -1 when only the exact kernel ran
  * (TPDM_ATTN_EXACT=1).  0 on ordinary activations: the exact pass then costs one empty launch. */
 int tpdm_attention_redo_count(void);
+/* the same, summed over every attention launch since the library was loaded (exact-only mode: 0) */
+long long tpdm_attention_redo_total(void);
 /* conv3x3 pad 1 over NHWC bf16 x [batch][g][g][C], w bf16 [N][9][C] -> out fp32 [batch][g*g][N] */
 int tpdm_conv3x3_nhwc(const void* x, const void* w, const float* bias, float* out, int batch, int g, int C, int N,
                       void* stream);

@@ -11,6 +11,7 @@ import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tpdm_b200 import _lib as _L  # noqa: E402
 from tpdm_b200.modeling_sd3_pnt import SD3_MEDIUM_TRANSFORMER_CONFIG, SD3PredictNextTimeStepModel  # noqa: E402
 
 seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 8.0
@@ -54,4 +55,4 @@ clk = sorted(s[0] for s in samples)
 pw = sorted(s[1] for s in samples)
 print(f"{os.environ.get('TPDM_B200_LIB', 'product')}{' exact-only' if os.environ.get('TPDM_ATTN_EXACT') == '1' else ''}: {images} images, {steps} steps, "
       f"{ms / steps:.3f} ms per denoising step, {images / ms * 1e3:.3f} images/s; median SM clock {clk[len(clk) // 2]:.0f} MHz, "
-      f"median power {pw[len(pw) // 2]:.0f} W", flush=True)
+      f"median power {pw[len(pw) // 2]:.0f} W; attention CTAs that took the exact pass: {_L.load().tpdm_attention_redo_total()}", flush=True)

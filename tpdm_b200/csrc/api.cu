@@ -769,6 +769,7 @@ int tpdm_joint_attention(const void* qkv, void* out, int Bt, int S, int H, int d
 }
 
 int tpdm_attention_redo_count(void) { return attn_redo_count(); }
+long long tpdm_attention_redo_total(void) { return attn_redo_total(); }
 
 int tpdm_conv3x3_nhwc(const void* x, const void* w, const float* bias, float* out, int batch, int g, int C, int N, void* stream) {
   TPDM_CHECK(x && w && out, TPDM_ERR_ARG, "tpdm_conv3x3_nhwc: null argument");

@@ -60,6 +60,13 @@ constexpr float kRescaleThreshold = 32.0f;  // log2 units
 #define TPDM_POLY_EVERY 4
 #endif
 constexpr int kPolyEvery = TPDM_POLY_EVERY;
+// Fast path, polynomial pairs: 0 = clamp the argument below and track its maximum (3 instructions per pair), 1 = only CHECK
+// |x| <= 126 with one FMNMX3 per pair and send the CTA to the exact pass otherwise.  Measured (profiles/r02_attention_experiments.txt):
+// 289.3 vs 291.1 us, 21.41 vs 21.44 ms per sustained denoising step -- no gain worth a performance cliff for rows that hold a
+// score 87 nats below their reference, so the clamp stays.
+#ifndef TPDM_ATTN_POLY_ABS
+#define TPDM_ATTN_POLY_ABS 0
+#endif
 // -DTPDM_ATTN_TRACE: clock64() time stamps of one CTA's softmax warp 4 (role 0, 8 slots per key tile) and of the two MMA-issuing
 // warps (roles 1 and 2, 4 slots per key tile), read back with tpdm_attn_trace_read (tools/attn_trace.py).  Diagnostic builds only.
 #ifdef TPDM_ATTN_TRACE
@@ -79,6 +86,8 @@ __device__ long long g_cta_trace[2][16];
 #define ATRACE(role, idx)
 #define CTRACE(idx)
 #endif
+
+__device__ unsigned long long g_redo_total;   // CTAs that took the exact pass since the library was loaded (tpdm_attention_redo_total)
 
 template <int DP>
 struct AttnSmem {
@@ -352,7 +361,7 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
       // polynomial, which would wrap instead of overflowing) -- sets this CTA's redo flag, and the CTA then runs its tile a second time with the
       // exact softmax (per-chunk maxima, the `else` branch below) before it exits.  Per 128 keys this removes 64 FMNMX3, four votes and the
       // serial "load chunk 0 -> maximum -> vote" prefix of every tile from the softmax warps.
-      constexpr float kSoft = 4294967296.f, kHard = 1.8446744073709552e19f, kPolyMax = 127.f;
+      constexpr float kSoft = 4294967296.f, kHard = 1.8446744073709552e19f, kPolyMax = 126.f;
       uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);   // row sum as four partial sums
       float pmax = -INFINITY;   // largest argument that went through the polynomial since the last guard
       bool hard = false;
@@ -379,7 +388,8 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
       }
 #endif
       // exponentials of one 32-column chunk, packed to bf16
-      auto exp_chunk = [&](const uint32_t (&v)[32], uint32_t (&pk)[16], const uint64_t negm2) {
+      auto exp_chunk = [&](const uint32_t (&v)[32], uint32_t (&pk)[16], const uint64_t negm2, auto clamp_tag) {
+        constexpr bool kClamp = decltype(clamp_tag)::value || !TPDM_ATTN_POLY_ABS;   // the masked tail tile holds -inf scores
         const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f), nmagic2 = pack_f32x2(-12582912.f, -12582912.f);
         const uint64_t mone2 = pack_f32x2(-1.f, -1.f);
         const uint64_t c0 = pack_f32x2(0.9999280572f, 0.9999280572f), c1 = pack_f32x2(0.6932609677f, 0.6932609677f),
@@ -389,8 +399,11 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
           float x0, x1, p0, p1;
           unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), scale2, negm2), x0, x1);
           if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
-            pmax = fmax3(pmax, x0, x1);
-            const uint64_t xp = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+            // Unmasked tiles, no clamp: |x| <= 126 is CHECKED (one FMNMX3 with |.| modifiers per pair instead of two clamps and a
+            // maximum); an argument outside -- a score 87 nats below the reference, or one the row-sum guard could not keep in
+            // range -- flags the CTA for the exact pass.  The masked tail tile clamps (its -inf scores are legitimate).
+            pmax = kClamp ? fmax3(pmax, x0, x1) : fmax3(pmax, fabsf(x0), fabsf(x1));
+            const uint64_t xp = kClamp ? pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f)) : pack_f32x2(x0, x1);
             const uint64_t t = fadd2(xp, magic2);
             const uint64_t fr = ffma2(fadd2(t, nmagic2), mone2, xp);
             uint64_t pp = ffma2(c3, fr, c2);
@@ -457,7 +470,7 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
           mask_chunk(0, va, valid);
           mask_chunk(1, vb, valid);
         }
-        exp_chunk(va, pk, negm2);
+        exp_chunk(va, pk, negm2, masked_tag);
         if (j > 0) {  // P is single-buffered: P(j-1) V must be done before P(j) lands
           mbar_wait(pv_done, (j - 1) & 1);
           tc_fence_after();
@@ -466,7 +479,7 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
         tmem_st_32x16(p_tmem, pk);
         tmem_ld_32x32(s_tmem + 2 * kChunk, va);
         STRACE(3);
-        exp_chunk(vb, pk, negm2);
+        exp_chunk(vb, pk, negm2, masked_tag);
         tmem_st_32x16(p_tmem + 16, pk);
         tmem_ld_32x32(s_tmem + 3 * kChunk, vb);
         // keys [0,64) of P(j) go to the MMA warp
@@ -484,9 +497,9 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
           mask_chunk(2, va, valid);
           mask_chunk(3, vb, valid);
         }
-        exp_chunk(va, pk, negm2);
+        exp_chunk(va, pk, negm2, masked_tag);
         tmem_st_32x16(p_tmem + 32, pk);
-        exp_chunk(vb, pk, negm2);
+        exp_chunk(vb, pk, negm2, masked_tag);
         tmem_st_32x16(p_tmem + 48, pk);
         tmem_wait_st();
         tc_fence_before();
@@ -676,6 +689,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   CTRACE(5);
   const int redo = redo_smem;
   if (redo != 0) {
+    if (threadIdx.x == 0) atomicAdd(&g_redo_total, 1ull);
     if (warp == 1 && lane == 0) B.init(true);
     tc_fence_before();
     __syncthreads();
@@ -801,6 +815,13 @@ int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int 
   TPDM_TRY(encode_tmap_bf16(&op->tmK, base + static_cast<size_t>(H) * dp, 4, dims, strides, box));
   TPDM_TRY(encode_tmap_bf16(&op->tmV, base + static_cast<size_t>(2) * H * dp, 4, dims, strides, box));
   return 0;
+}
+
+long long attn_redo_total() {
+  unsigned long long v = 0;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+  if (cudaMemcpyFromSymbol(&v, g_redo_total, sizeof(v)) != cudaSuccess) return -2;
+  return static_cast<long long>(v);
 }
 
 int attn_redo_count() {

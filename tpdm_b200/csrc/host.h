@@ -143,6 +143,7 @@ struct alignas(64) AttnOp {
 };
 int attn_op_init(AttnOp* op, const void* qkv, int Bt, int S, int H, int dp, int head_dim, void* out);
 int attn_launch(const AttnOp* op, cudaStream_t stream);
+long long attn_redo_total();  // diagnostic, synchronises: CTAs that took the exact pass since the library was loaded
 int attn_redo_count();  // diagnostic, synchronises: CTAs of the last launch recomputed by the exact kernel (-1: exact only)
 
 }  // namespace tpdm

@@ -115,6 +115,19 @@ class ClockSampler:
 NCU_DRAM_BYTES_PER_LAUNCH = {"gemm_bf16_tcgen05": 136.1e6, "joint_attention_tcgen05": 91.9e6}
 
 
+# sm__pipe_tensor_cycles_active (% of active cycles) from the round-2 `ncu --set full` captures: the CTA-pair GEMM on the four block
+# shapes (profiles/r02_gemm2_vs_cublas_ncu.txt: QKV 87, FF1 90, FF2 86, out-proj 60; FLOP-weighted over a block) and the fast attention
+# kernel (profiles/r02_attention_fast_ncu.txt: 41.6)
+NCU_TENSOR_PIPE_ACTIVE = {"gemm_bf16_tcgen05": (125 * 87 + 167 * 90 + 167 * 86 + 42 * 60) / 501.0, "joint_attention_tcgen05": 41.6}
+
+
+def tensor_pipe_estimate(kernels: dict) -> dict:
+    """Whole-step tensor-pipe activity: the ncu per-kernel percentages weighted with this run's per-kernel share of the step."""
+    pct = sum(NCU_TENSOR_PIPE_ACTIVE[k] * v["share_of_trajectory"] for k, v in kernels.items() if k in NCU_TENSOR_PIPE_ACTIVE)
+    return {"pct_of_step": pct, "per_kernel_pct_ncu": NCU_TENSOR_PIPE_ACTIVE,
+            "how": "ncu sm__pipe_tensor_cycles_active per kernel (stand-alone captures) x share of the sampled trajectory (this run)"}
+
+
 def mmdit_flops_1024() -> float:
     from oracle.sd3_oracle import mmdit_flops, sd3_medium_config
 
@@ -289,6 +302,10 @@ def run_ours(args, rank, world, local_rank):
         kernels=kernels, hbm_kernels=hbm, kernel_time_share_of_trajectory=sum(k["share_of_trajectory"] for k in list(kernels.values()) + list(hbm.values())),
         sampled_over=f"one extra trajectory ({prof_steps} denoising steps) with per-launch CUDA events; {dropped} launches of the speculatively "
                      "enqueued last step were skipped on the device and are not credited",
+        kernel_time_share_note="the share sums the FOUR bracketed kernel classes only (GEMM, attention, LayerNorm-modulate, adaLN GEMV); the other "
+                               "~14 small kernels of a step are 1.5 % of its kernel time in the ncu launch list (profiles/r02_launch_shares*.txt), and "
+                               "the event brackets themselves break programmatic-dependent-launch overlap in this sampled trajectory",
+        tensor_pipe_active_estimate=tensor_pipe_estimate(kernels),
         tensor_pipe_note="sm__pipe_tensor_cycles_active per kernel: profiles/ (ncu); this line reports algorithmic FLOP/s over the sustained peak")
     line = {
         "metric": METRIC, "value": world * K / (ms_value / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

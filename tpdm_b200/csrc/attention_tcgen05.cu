@@ -27,11 +27,19 @@
 //    pipelined (the load of chunk c+1 is in flight while chunk c is exponentiated).
 //  * tools/microbench/tmem_read_rate.cu: tcgen05.ld moves 490-1050 B/clk/SM, so reading S back in fp32 is NOT a floor (round 1
 //    assumed 64 B/clk/SM); the floor of this kernel is the MUFU: 16 ex2 / clk / SM = 1024 cycles per 128 x 128 scores.
-// Softmax: fp32, exp2 with log2(e)/sqrt(d) folded into one FFMA2, against a reference maximum m_used that is raised lazily: every
-// 32-column chunk computes its own maximum (FMNMX3 trees, issued under the MUFU work of the previous chunk) and only when that
-// exceeds m_used by more than 2^kRescaleThreshold does the row take the (rare, exact) path that moves the reference and rescales
-// what was accumulated under the old one -- O, l and the P chunks of this tile already stored.  fp32 sums and bf16 P carry 8 exponent bits, so running up
-// to 2^32 above the reference costs no precision, and the final 1/l cancels the reference.
+// Softmax: fp32, exp2 with log2(e)/sqrt(d) folded into one FFMA2, in two flavours (attn_cta<DP, kFast>):
+//  * FAST (what joint_attention_fast_kernel runs first).  No maximum inside the key loop: the reference m_ref only has to keep
+//    exp2(s - m_ref) inside the fp32 / bf16 exponent range.  It starts as the row maximum of the first key tile and is guarded by
+//    the ROW SUM the loop computes anyway: at the top of a tile, l > 2^32 moves it up by floor(log2 l) (O and l rescaled by that
+//    power of two; no P of the new tile exists yet).  A row the guard cannot keep in range (l > 2^64, inf, NaN, or an argument
+//    > 127 reaching the polynomial, which would wrap instead of overflowing) flags the CTA.
+//  * EXACT (a flagged CTA reruns its tile with it before it exits; TPDM_ATTN_EXACT=1 runs it alone).  Reference maximum m_used raised
+//    lazily: every 32-column chunk computes its own maximum (FMNMX3 trees, issued under the MUFU work of the previous chunk) and
+//    only when that exceeds m_used by more than 2^kRescaleThreshold does the row take the (rare, exact) path that moves the
+//    reference and rescales what was accumulated under the old one -- O, l and the P chunks of this tile already stored.
+// fp32 sums and bf16 P carry 8 exponent bits, so running up to 2^32 above the reference costs no precision, and the final 1/l cancels
+// the reference.  Round-2 measurements (B200, S = 4429, H = 24, Bt = 2): exact 320-327 us, fast 288-292 us (cuDNN SDPA: 283 us);
+// everything tried on the way is in profiles/r02_attention_experiments.txt.
 #include <cuda_bf16.h>
 
 #include <stdlib.h>

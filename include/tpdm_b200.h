@@ -171,6 +171,11 @@ int tpdm_sample_begin(tpdm_plan* plan, const float* latents, const float* neg_em
                       const float* ratios, unsigned long long seed, void* stream);
 /* one denoising step `step` (0-based): MMDiT -> CFG -> TPM -> schedule update -> Euler.  No host synchronisation. */
 int tpdm_sample_step(tpdm_plan* plan, int step, void* stream);
+/* the same step replayed from a CUDA graph: one graph per step index, captured the first time that step runs on this plan and
+ * kept while guidance_scale / predict / injected ratios stay as they were (the stream must not be the legacy default stream).
+ * Trajectories that draw their ratios on the device (predict == 0 without `ratios`: the seed is a kernel argument) and calls made
+ * while tpdm_profile_start is active run the plain step. */
+int tpdm_sample_step_graph(tpdm_plan* plan, int step, void* stream);
 /* device-resident results; all [batch][max_steps] row-major unless stated */
 typedef struct tpdm_sample_state {
   float* latents;        /* [batch][C][h][w] current latents (fp32 master copy) */

@@ -408,6 +408,29 @@ def test_tiny_injected_ratios_vs_golden(golden):
         model.only_predict_logprobs(None, None, None)
 
 
+@pytest.mark.parametrize("predict", [True, False])
+def test_graph_replayed_steps_equal_plain_steps(predict):
+    """Engine.sample replays every step index from a CUDA graph (tpdm_sample_step_graph).  Capture (first trajectory), replay (second
+    trajectory, other latents and guidance -> graphs dropped and re-captured; third: pure replay) and the plain launch path must give
+    bit-identical trajectories; injected ratios go through the graphs too, device-side draws (seed argument) take the plain path."""
+    pipe, inp, model = _tiny()
+    eng = model.get_engine()
+    g = torch.Generator().manual_seed(5)
+    cu = {k: v.cuda() for k, v in inp.items()}
+    args = (cu["prompt_embeds"], cu["negative_prompt_embeds"], cu["pooled_prompt_embeds"], cu["negative_pooled_prompt_embeds"])
+    ratios = None if predict else (0.55 + 0.4 * torch.rand(2, 8, generator=g)).cuda()
+    keys = ("sigmas", "alphas", "betas", "logprobs_raw", "history_latents", "tembs")
+    for trial, (gs, lat) in enumerate(((7.0, cu["latents"]), (3.5, cu["latents"] * 0.5 + 0.1), (3.5, cu["latents"].flip(0)))):
+        runs = [eng.sample(lat, *args, 8, gs, predict, ratios=ratios, record_velocity=True, use_graph=ug) for ug in (True, False, True)]
+        for k in keys + ("velocities",):
+            assert torch.equal(runs[0][k], runs[1][k]) and torch.equal(runs[2][k], runs[1][k]), (trial, k)
+        assert runs[0]["steps"] == runs[1]["steps"]
+    # device-side Beta draws: same seed -> same trajectory with and without use_graph (both run the plain step)
+    a = eng.sample(cu["latents"], *args, 6, 7.0, False, seed=11, use_graph=True)
+    b = eng.sample(cu["latents"], *args, 6, 7.0, False, seed=11, use_graph=False)
+    assert torch.equal(a["sigmas"], b["sigmas"]) and torch.equal(a["history_latents"], b["history_latents"])
+
+
 def test_tiny_early_termination_and_device_sampler():
     """min_sigma high enough that the batch finishes before max steps: loop must stop exactly like the reference
     (one masked step after sigma < min_sigma) and device-side Beta draws must be valid and seed-reproducible."""

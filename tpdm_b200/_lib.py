@@ -80,6 +80,7 @@ EXPORTS = {
     "tpdm_euler_step": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_longlong, vp]),
     "tpdm_sample_begin": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_float, C.c_int, vp, C.c_ulonglong, vp]),
     "tpdm_sample_step": (C.c_int, [vp, C.c_int, vp]),
+    "tpdm_sample_step_graph": (C.c_int, [vp, C.c_int, vp]),
     "tpdm_sample_state_get": (C.c_int, [vp, C.POINTER(TpdmSampleState)]),
     "tpdm_tpm_param_offsets": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_longlong)]),
     "tpdm_tpm_trainer_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

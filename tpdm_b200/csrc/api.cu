@@ -84,8 +84,21 @@ struct tpdm_plan {
     cudaGraphExec_t graph = nullptr;   // one captured queue step (every pointer of a queue step is fixed between steps)
     long long graph_launches = 0;
   } q;
+  // tpdm_sample_step_graph: one captured graph per step index (the step index only moves pointers inside the plan's own buffers),
+  // valid for the guidance / predict / injected-ratio setting they were captured under
+  std::vector<cudaGraphExec_t> step_graph;
+  std::vector<long long> step_graph_launches;
+  float graph_guidance = 0.f;
+  int graph_predict = -1, graph_have_ratios = -1;
+  void drop_step_graphs() {
+    for (cudaGraphExec_t g : step_graph)
+      if (g) cudaGraphExecDestroy(g);
+    step_graph.clear();
+    step_graph_launches.clear();
+  }
   ~tpdm_plan() {
     if (q.graph) cudaGraphExecDestroy(q.graph);
+    drop_step_graphs();
   }
 };
 
@@ -548,6 +561,46 @@ int tpdm_sample_step(tpdm_plan* p, int step, void* stream) {
   TPDM_TRY(k_schedule(a, s));
   TPDM_TRY(k_unpatchify(p->pout, B, 1, p->guidance, ctx->cfg.out_channels, p->Hl, p->Wl, p->velocity, p->latents, p->sigma_hist + step,
                         p->sigma_hist + step + 1, T1, p->history + static_cast<size_t>(step) * lat, s));
+  return 0;
+}
+
+int tpdm_sample_step_graph(tpdm_plan* p, int step, void* stream) {
+  TPDM_CHECK(p, TPDM_ERR_ARG, "tpdm_sample_step_graph: null plan");
+  TPDM_CHECK(p->begun, TPDM_ERR_STATE, "tpdm_sample_step_graph: call tpdm_sample_begin first");
+  TPDM_CHECK(step >= 0 && step < p->max_steps, TPDM_ERR_ARG, "tpdm_sample_step_graph: step %d outside [0,%d)", step, p->max_steps);
+  // The Philox seed of a sampled trajectory is a kernel argument that changes with every call, and per-launch profiling records
+  // events on the stream: both take the plain path.  (predict / injected ratios never read the seed.)
+  if ((!p->predict && !p->have_ratios) || profiling_active()) return tpdm_sample_step(p, step, stream);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (p->graph_guidance != p->guidance || p->graph_predict != p->predict || p->graph_have_ratios != p->have_ratios) {
+    p->drop_step_graphs();
+    p->graph_guidance = p->guidance;
+    p->graph_predict = p->predict;
+    p->graph_have_ratios = p->have_ratios;
+  }
+  if (p->step_graph.empty()) {
+    p->step_graph.assign(p->max_steps, nullptr);
+    p->step_graph_launches.assign(p->max_steps, 0);
+  }
+  if (p->step_graph[step] == nullptr) {
+    const long long before = launches_so_far();
+    cudaGraph_t g = nullptr;
+    TPDM_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int st = tpdm_sample_step(p, step, s);
+    const cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (st != 0) {
+      if (g) cudaGraphDestroy(g);
+      return st;
+    }
+    TPDM_CHECK(e == cudaSuccess && g != nullptr, TPDM_ERR_CUDA, "tpdm_sample_step_graph: stream capture failed: %s", cudaGetErrorString(e));
+    const cudaError_t ei = cudaGraphInstantiate(&p->step_graph[step], g, 0);
+    cudaGraphDestroy(g);
+    TPDM_CHECK(ei == cudaSuccess, TPDM_ERR_CUDA, "tpdm_sample_step_graph: cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+    p->step_graph_launches[step] = launches_so_far() - before;
+    count_launches(-p->step_graph_launches[step]);  // the capture itself launched nothing
+  }
+  TPDM_CUDA_OK(cudaGraphLaunch(p->step_graph[step], s));
+  count_launches(p->step_graph_launches[step]);
   return 0;
 }
 

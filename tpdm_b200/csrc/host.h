@@ -40,6 +40,7 @@ int num_sms();
 void count_launch();
 void count_launches(long long n);  // kernels replayed through a CUDA graph
 long long launches_so_far();
+bool profiling_active();  // between tpdm_profile_start and tpdm_profile_stop
 void prof_begin(int cls, double flops, cudaStream_t s);
 void prof_end(cudaStream_t s);
 

@@ -61,6 +61,8 @@ struct Profiler {
 Profiler g_prof;
 }  // namespace
 
+bool profiling_active() { return g_prof.on; }
+
 void prof_begin(int cls, double flops, cudaStream_t s) {
   if (!g_prof.on || 2 * (g_prof.n + 1) > g_prof.ev.size()) return;
   g_prof.cls[g_prof.n] = cls;

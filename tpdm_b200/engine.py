@@ -5,6 +5,7 @@ operation of the path runs inside the C-ABI library (no eager fallback exists).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -310,10 +311,15 @@ class Engine:
     # ---- the adaptive loop -------------------------------------------------------------------------------------
     def sample(self, latents, prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds,
                max_inference_steps: int, guidance_scale: float, predict: bool, ratios=None, seed: int = 0,
-               record_tpm_inputs: bool = False, record_velocity: bool = False):
+               record_tpm_inputs: bool = False, record_velocity: bool = False, use_graph: Optional[bool] = None):
         """Runs tpdm_sample_step until every sigma_next < min_sigma (checked one step late through a pinned flag, the
-        speculative extra step is skipped on the device) or max_inference_steps.  Returns a dict of device tensors."""
+        speculative extra step is skipped on the device) or max_inference_steps.  Returns a dict of device tensors.
+        ``use_graph`` (default: on, ``TPDM_SAMPLE_GRAPH=0`` turns it off): every step index is replayed from a CUDA graph
+        captured the first time it runs on the plan (~190 launches become one ``cudaGraphLaunch``); the trajectory then runs on a
+        side stream, because the legacy default stream cannot be captured, and the caller's stream waits for it."""
         lib = L.load()
+        if use_graph is None:
+            use_graph = os.environ.get("TPDM_SAMPLE_GRAPH", "1") != "0"
         B, Cc, h, w = latents.shape
         dev, f32 = self.device, torch.float32
         plan = self.plan(B, True, h, prompt_embeds.shape[1], max_inference_steps)
@@ -338,12 +344,19 @@ class Engine:
         if events is None:
             events = self._step_events = [torch.cuda.Event(), torch.cuda.Event()]
         executed = max_inference_steps
-        with torch.cuda.device(dev):
+        step_fn = lib.tpdm_sample_step_graph if use_graph else lib.tpdm_sample_step
+        side = None
+        if use_graph:
+            side = getattr(self, "_sample_stream", None)
+            if side is None:
+                side = self._sample_stream = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.device(dev), torch.cuda.stream(side):
             stream = L.stream_ptr()
             L.check(lib.tpdm_sample_begin(plan.handle, L.ptr(lat), L.ptr(ne), L.ptr(pe), L.ptr(npp), L.ptr(pp), float(guidance_scale),
                                           1 if predict else 0, L.ptr(rt) if rt is not None else None, int(seed) & (2**64 - 1), stream))
             for step in range(max_inference_steps):
-                L.check(lib.tpdm_sample_step(plan.handle, step, stream))
+                L.check(step_fn(plan.handle, step, stream))
                 if rec is not None:
                     rec[:, step].copy_(st["tpm_input"])
                 if vel is not None:
@@ -357,6 +370,11 @@ class Engine:
                         break
             else:
                 events[(max_inference_steps - 1) & 1].synchronize()
+        if side is not None:
+            torch.cuda.current_stream(dev).wait_stream(side)
+            for t in (lat, pe, ne, pp, npp, rt, rec, vel):
+                if t is not None:
+                    t.record_stream(side)
         T = executed
         out = dict(
             steps=T,

@@ -75,6 +75,13 @@ constexpr int kPolyEvery = TPDM_POLY_EVERY;
 #ifndef TPDM_ATTN_POLY_ABS
 #define TPDM_ATTN_POLY_ABS 0
 #endif
+// Fast path experiment: 1 = P is converted to bf16 by TRUNCATION (one PRMT per pair on the ALU pipe) instead of F2FP.BF16.PACK_AB,
+// which runs on the XU pipe next to MUFU.EX2, with the mean loss of 2^-10 / ln 2 per element (log-uniform mantissas) divided out of
+// the row sum in the epilogue.  Takes a quarter of the XU work away and gains 1.7 % (287.0 vs 292.0 us; 21.13 vs 21.21 ms per
+// sustained step) at a rel-L2 error of 2.78e-3 instead of 2.34e-3: the XU pipe is not the bound either, and the rounding stays.
+#ifndef TPDM_ATTN_TRUNC_P
+#define TPDM_ATTN_TRUNC_P 0
+#endif
 // -DTPDM_ATTN_TRACE: clock64() time stamps of one CTA's softmax warp 4 (role 0, 8 slots per key tile) and of the two MMA-issuing
 // warps (roles 1 and 2, 4 slots per key tile), read back with tpdm_attn_trace_read (tools/attn_trace.py).  Diagnostic builds only.
 #ifdef TPDM_ATTN_TRACE
@@ -428,7 +435,11 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
           }
           if (i & 1) lb = fadd2(lb, pack_f32x2(p0, p1));
           else la = fadd2(la, pack_f32x2(p0, p1));
+#if TPDM_ATTN_TRUNC_P
+          pk[i] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632);   // upper halves: bf16 by truncation (one PRMT, ALU pipe)
+#else
           pk[i] = pack_bf16x2(p0, p1);
+#endif
         }
       };
       auto row_sum = [&]() {
@@ -623,7 +634,7 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
     const int row = q0 + q * 32 + lane;
-    const float inv_l = 1.0f / l;
+    const float inv_l = (kFast && TPDM_ATTN_TRUNC_P) ? 1.0f / (l * (1.0f - 0.00140887f)) : 1.0f / l;
     __nv_bfloat16* out = A.out + (static_cast<long long>(b) * A.S + row) * (static_cast<long long>(A.H) * DP) + h * DP;
 #pragma unroll
     for (int c = 0; c < DP / 32; ++c) {

@@ -191,6 +191,50 @@ if __name__ == "__main__":
             mhz = sorted(c for c, _ in late)[len(late) // 2] if late else float("nan")
             pw = max((p for _, p in late), default=float("nan"))
             print(f"{name:13s} {rows}x{N}x{K}: {2.0*rows*N*K*n/ms/1e9:7.1f} TFLOP/s sustained over {ms/1e3:.1f} s, median SM clock {mhz:.0f} MHz, max power {pw:.0f} W", flush=True)
+    if which == "attn_sustained":   # 4 s of the SD3-medium attention kernel back to back, and of cuDNN SDPA on the same shape: clocks and power
+        import subprocess, threading
+        Bt, S, H, d = 2, 4429, 24, 64
+        qkv = torch.randn(Bt, S, 3, H, d, device=dev).bfloat16().contiguous()
+        out = torch.zeros(Bt, S, H, d, device=dev, dtype=torch.bfloat16)
+        qf, kf, vf = (qkv[:, :, i].transpose(1, 2).contiguous() for i in range(3))
+        def ours():
+            lib.tpdm_joint_attention(L.ptr(qkv), L.ptr(out), Bt, S, H, 64, d, 0, None)
+        def sdpa():
+            torch.nn.functional.scaled_dot_product_attention(qf, kf, vf)
+        for name, fn in (("tpdm attention", ours), ("torch SDPA", sdpa), ("tpdm attention", ours)):
+            clocks, stop = [], [False]
+            def sample():
+                while not stop[0]:
+                    r = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits"], capture_output=True, text=True)
+                    try:
+                        c, pw = r.stdout.strip().split(",")
+                        clocks.append((float(c), float(pw)))
+                    except Exception:
+                        pass
+                    time.sleep(0.2)
+            th = threading.Thread(target=sample, daemon=True)
+            for _ in range(20):
+                fn()
+            torch.cuda.synchronize()
+            th.start()
+            n, t0 = 0, time.perf_counter()
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            while time.perf_counter() - t0 < 4.0:
+                for _ in range(100):
+                    fn()
+                n += 100
+                torch.cuda.synchronize()
+            e1.record()
+            torch.cuda.synchronize()
+            stop[0] = True
+            th.join()
+            ms = e0.elapsed_time(e1)
+            late = clocks[len(clocks) // 2:]
+            mhz = sorted(c for c, _ in late)[len(late) // 2] if late else float("nan")
+            pw = sorted(p for _, p in late)[len(late) // 2] if late else float("nan")
+            print(f"{name:15s} Bt={Bt} H={H} S={S} d={d}: {ms / n * 1e3:7.1f} us per launch = {4.0*Bt*H*S*S*d*n/ms/1e9:7.1f} TFLOP/s sustained over {ms/1e3:.1f} s, "
+                  f"median SM clock {mhz:.0f} MHz, median power {pw:.0f} W", flush=True)
     if which == "ln":
         for (batch, rows) in ((2, 4096), (2, 333)):
             D = 1536

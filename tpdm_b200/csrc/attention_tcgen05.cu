@@ -53,7 +53,17 @@ namespace tpdm {
 
 namespace {
 
+// Fast path experiment: 1 = EIGHT softmax warps per CTA (384 threads, 80 registers): warps 4-7 take keys [0,64) of every tile, warps
+// 8-11 keys [64,128) of the same rows (a warp reaches the TMEM lanes 32 * (warp % 4) ..., so the pairs (4,8), (5,9), ... share rows).
+// Four softmax warps per scheduler instead of two.  Both halves of a row must use ONE reference: every 4th tile a half whose partial
+// row sum has passed 2^24 proposes a shift through shared memory and both apply it at the next checkpoint (see `tile` in the split branch).  16-column chunks
+// (two buffers of 16 registers).
+#ifndef TPDM_ATTN_SPLIT
+#define TPDM_ATTN_SPLIT 0
+#endif
 constexpr int kAttnThreads = 256;
+constexpr bool kSplit = TPDM_ATTN_SPLIT != 0;
+constexpr int kFastThreads = kSplit ? 384 : 256;   // fast kernel: 4 control warps + 4 or 8 softmax warps
 constexpr int kQT = 128;   // query rows per CTA
 constexpr int kKT = 128;   // keys per K/V smem tile = keys per S tile
 constexpr int kChunk = 32; // S columns per tcgen05.ld
@@ -138,7 +148,7 @@ struct AttnBars {
   }
   static constexpr int kCount = 1 + 4 * kKVStages + 5;
   // one thread; `again`: the barriers carry the phases of a finished tile (persistent exact kernel) and are invalidated first
-  __device__ void init(bool again) const {
+  __device__ void init(bool again, uint32_t s_free_count = 4) const {
     if (again) {
       for (int i = 0; i < kCount; ++i) mbar_inval(q_full + i);
     }
@@ -150,7 +160,7 @@ struct AttnBars {
       mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 4);
+    mbar_init(s_free, s_free_count);
     mbar_init(&p_full[0], 4);
     mbar_init(&p_full[1], 4);
     mbar_init(pv_done, 1);
@@ -267,7 +277,207 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
       __syncwarp();
     }
   }
-  } else {
+  } else if (kFast && kSplit) {
+    // ---------------------------------------------------------------- split fast softmax: warps 4-7 keys [0,64), warps 8-11 keys [64,128)
+    __shared__ float xch[2][kQT];
+    __shared__ int bump[2][kQT];   // see `tile`: total reference shift (float bits, >= 0) in force from the tiles of one parity on
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t s_tmem = tmem_base + lane_off + L::kSCol + half * 64;
+    const uint32_t p_tmem = tmem_base + lane_off + L::kPCol + half * 32;
+    const uint32_t o_tmem = tmem_base + lane_off + L::kOCol + half * (DP / 2);
+    const int rowi = q * 32 + lane;
+    const float scale = A.scale_log2;
+    const uint64_t scale2 = pack_f32x2(scale, scale);
+    constexpr float kSoft = 4294967296.f, kHard = 1.8446744073709552e19f, kPolyMax = 127.f;
+    uint64_t la = pack_f32x2(0.f, 0.f), lb = pack_f32x2(0.f, 0.f);
+    float pmax = -INFINITY;
+    bool hard = false;
+    float applied = 0.f;   // total shift applied to this thread's reference
+    if (half == 0) {
+      bump[0][q * 32 + lane] = 0;
+      bump[1][q * 32 + lane] = 0;
+    }
+    auto mask16 = [&](const int c, uint32_t (&v)[16], const int valid) {   // keys >= S of the tail tile
+      if (valid < kKT) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (half * 64 + c * 16 + e >= valid) v[e] = 0xff800000u;
+      }
+    };
+    // reference = row maximum of the first key tile (both halves, exchanged through shared memory once)
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float m_ref;
+    {
+      const int valid0 = A.S < kKT ? A.S : kKT;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(s_tmem + c * 16, v);
+        tmem_wait_ld();
+        mask16(c, v, valid0);
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) mx = fmax3(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+      }
+      xch[half][rowi] = mx * scale;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      m_ref = fmaxf(xch[0][rowi], xch[1][rowi]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // xch is reused for the row sums
+    }
+    uint64_t negm2 = pack_f32x2(-m_ref, -m_ref);
+    auto exp16 = [&](const uint32_t (&v)[16], uint32_t (&pk)[8]) {
+      const uint64_t magic2 = pack_f32x2(12582912.f, 12582912.f), nmagic2 = pack_f32x2(-12582912.f, -12582912.f);
+      const uint64_t mone2 = pack_f32x2(-1.f, -1.f);
+      const uint64_t c0 = pack_f32x2(0.9999280572f, 0.9999280572f), c1 = pack_f32x2(0.6932609677f, 0.6932609677f),
+                     c2 = pack_f32x2(0.2426111251f, 0.2426111251f), c3 = pack_f32x2(0.0551716499f, 0.0551716499f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x0, x1, p0, p1;
+        unpack_f32x2(ffma2(pack_f32x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), scale2, negm2), x0, x1);
+        if (kPolyEvery > 0 && (i % (kPolyEvery > 0 ? kPolyEvery : 1)) == (kPolyEvery - 1)) {
+          pmax = fmax3(pmax, x0, x1);
+          const uint64_t xp = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+          const uint64_t t = fadd2(xp, magic2);
+          const uint64_t fr = ffma2(fadd2(t, nmagic2), mone2, xp);
+          uint64_t pp = ffma2(c3, fr, c2);
+          pp = ffma2(pp, fr, c1);
+          pp = ffma2(pp, fr, c0);
+          float t0, t1;
+          unpack_f32x2(t, t0, t1);
+          unpack_f32x2(pp, p0, p1);
+          p0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+          p1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+        } else {
+          p0 = exp2_approx(x0);
+          p1 = exp2_approx(x1);
+        }
+        if (i & 1) lb = fadd2(lb, pack_f32x2(p0, p1));
+        else la = fadd2(la, pack_f32x2(p0, p1));
+        pk[i] = pack_bf16x2(p0, p1);
+      }
+    };
+    auto row_sum = [&]() {
+      float a0, a1, b0, b1;
+      unpack_f32x2(la, a0, a1);
+      unpack_f32x2(lb, b0, b1);
+      return (a0 + a1) + (b0 + b1);
+    };
+    auto tile = [&](const int j, auto masked_tag) {
+      constexpr bool kMasked = decltype(masked_tag)::value;
+      const int valid = A.S - j * kKT;
+      // Both halves of a row must move their reference at the SAME tile, so the guard runs at CHECKPOINTS (every 4th tile, the same
+      // tiles for every thread) through two shared-memory slots per row that hold a TOTAL shift (float bits, only ever raised by
+      // atomicMax: no slot needs clearing, and the larger of two simultaneous proposals wins for both halves).  At checkpoint c
+      // a thread applies the total it finds in slot c & 1 -- the proposals of checkpoint c - 1 -- and, if its own partial sum has
+      // passed 2^24, proposes applied + floor(log2 l) into slot (c + 1) & 1.  All of this sits BEHIND the wait for s_full(j): that
+      // wait is ordered after every softmax warp's s_free arrivals of the earlier tiles, so the proposals of the last checkpoint
+      // are visible and nobody still reads the slot that is written now.  A proposal takes effect 4 tiles later and up to 8 tiles
+      // after the sum started to grow: the 2^40 between the proposal threshold and the exact-pass threshold cover that.
+      hard = hard || pmax > kPolyMax;
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      if (warp == 4 && lane == 0) mbar_arrive(&k_empty[j % kKVStages]);
+      uint32_t va[16], vb[16], pk[8];
+      tmem_ld_32x16(s_tmem, va);
+      tmem_ld_32x16(s_tmem + 16, vb);
+      if ((j & 3) == 3) {
+        const int c = j >> 2;
+        const float lsum = row_sum();
+        const float total = __int_as_float(bump[c & 1][rowi]);
+        const bool over = !(lsum <= 16777216.f);
+        hard = hard || !(lsum <= kHard);
+        if (__any_sync(0xffffffffu, over || total > applied)) {   // rare; whole warp, rows without a shift use alpha = 1
+          const float e = total > applied ? total - applied : 0.f;
+          if (over && lsum <= kHard)   // the sum as it will stand after the shift applied right below
+            atomicMax(&bump[(c + 1) & 1][rowi],
+                      __float_as_int(fmaxf(total, applied) + fmaxf(static_cast<float>((__float_as_int(lsum) >> 23) - 127) - e, 0.f)));
+          const float m_new = m_ref + e;
+          const float alpha = exp2_approx(m_ref - m_new);
+          m_ref = m_new;
+          applied = fmaxf(total, applied);
+          negm2 = pack_f32x2(-m_ref, -m_ref);
+          mbar_wait(pv_done, (j - 1) & 1);   // every P V issued so far has drained: O may be touched
+          tc_fence_after();
+#pragma unroll 1
+          for (int cc = 0; cc < DP / 32; ++cc) {   // this half's DP / 2 columns of O
+            uint32_t o[16];
+            tmem_ld_32x16(o_tmem + cc * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x16(o_tmem + cc * 16, o);
+          }
+          const uint64_t alpha2 = pack_f32x2(alpha, alpha);
+          la = fmul2(la, alpha2);
+          lb = fmul2(lb, alpha2);
+        }
+      }
+      tmem_wait_ld();
+      if (kMasked) {
+        mask16(0, va, valid);
+        mask16(1, vb, valid);
+      }
+      exp16(va, pk);
+      if (j > 0) {  // P is single-buffered: P(j-1) V must be done before P(j) lands
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (warp == 4 && lane == 0) mbar_arrive(&v_empty[(j - 1) % kKVStages]);
+      }
+      tmem_st_32x8(p_tmem, pk);
+      tmem_ld_32x16(s_tmem + 32, va);
+      exp16(vb, pk);
+      tmem_st_32x8(p_tmem + 8, pk);
+      tmem_ld_32x16(s_tmem + 48, vb);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);   // this warp's half of S(j) is in registers (8 arrivals complete the phase)
+      if (kMasked) {
+        mask16(2, va, valid);
+        mask16(3, vb, valid);
+      }
+      exp16(va, pk);
+      tmem_st_32x8(p_tmem + 16, pk);
+      exp16(vb, pk);
+      tmem_st_32x8(p_tmem + 24, pk);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[half]);   // keys [0,64) from warps 4-7, keys [64,128) from warps 8-11: 4 arrivals each
+    };
+    for (int j = 0; j < n_kv - 1; ++j) tile(j, std::false_type{});
+    tile(n_kv - 1, std::true_type{});
+    const float lh = row_sum();
+    if (!(lh <= kHard) || pmax > kPolyMax) hard = true;
+    if (hard) *redo_smem = 1;
+    xch[half][rowi] = lh;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv_l = 1.0f / (xch[0][rowi] + xch[1][rowi]);
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const int row = q0 + rowi;
+    __nv_bfloat16* out = A.out + (static_cast<long long>(b) * A.S + row) * (static_cast<long long>(A.H) * DP) + h * DP + half * (DP / 2);
+#pragma unroll
+    for (int c = 0; c < DP / 64; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(o_tmem + c * 32, o);
+      tmem_wait_ld();
+      if (row < A.S) {
+        uint4* dst = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * e + 0]) * inv_l, __uint_as_float(o[8 * e + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv_l, __uint_as_float(o[8 * e + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv_l, __uint_as_float(o[8 * e + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv_l, __uint_as_float(o[8 * e + 7]) * inv_l);
+          dst[e] = w;
+        }
+      }
+    }
+  } else if (warp < 8) {
     // ---------------------------------------------------------------- softmax / correction / epilogue
     const int q = warp & 3;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
@@ -665,7 +875,7 @@ __device__ __forceinline__ void attn_cta(const AttnOp& A, uint8_t* smem, const i
 // range (see attn_cta) runs its tile a second time with the exact softmax (per-chunk maxima) before it exits -- same TMEM block,
 // mbarriers re-initialised.  On ordinary activations no CTA does.
 template <int DP>
-__global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attention_fast_kernel(const __grid_constant__ AttnOp A) {
+__global__ void __launch_bounds__(kFastThreads, DP == 64 ? 2 : 1) joint_attention_fast_kernel(const __grid_constant__ AttnOp A) {
   using L = AttnSmem<DP>;
   pdl_launch_dependents();
   uint8_t* smem = attn_smem_base();
@@ -686,7 +896,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
     tma_prefetch_desc(&A.tmK);
     tma_prefetch_desc(&A.tmV);
   }
-  if (warp == 1 && lane == 0) B.init(false);
+  if (warp == 1 && lane == 0) B.init(false, kSplit ? 8 : 4);
   if (threadIdx.x == 0) redo_smem = 0;
   pdl_wait();
   CTRACE(1);
@@ -709,7 +919,7 @@ __global__ void __launch_bounds__(kAttnThreads, DP == 64 ? 2 : 1) joint_attentio
   const int redo = redo_smem;
   if (redo != 0) {
     if (threadIdx.x == 0) atomicAdd(&g_redo_total, 1ull);
-    if (warp == 1 && lane == 0) B.init(true);
+    if (warp == 1 && lane == 0) B.init(true, 4);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -802,7 +1012,7 @@ int attn_launch_impl(const AttnOp& op, cudaStream_t stream) {
   if (exact_only())
     TPDM_CUDA_OK(launch_pdl(joint_attention_exact_kernel<DP>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
   else
-    TPDM_CUDA_OK(launch_pdl(joint_attention_fast_kernel<DP>, grid, dim3(kAttnThreads), AttnSmem<DP>::kTotal, stream, op));
+    TPDM_CUDA_OK(launch_pdl(joint_attention_fast_kernel<DP>, grid, dim3(kFastThreads), AttnSmem<DP>::kTotal, stream, op));
   prof_end(stream);
   count_launch();
   TPDM_CUDA_OK(cudaGetLastError());

@@ -117,7 +117,7 @@ NCU_DRAM_BYTES_PER_LAUNCH = {"gemm_bf16_tcgen05": 136.1e6, "joint_attention_tcge
 
 # sm__pipe_tensor_cycles_active (% of active cycles) from the round-2 `ncu --set full` captures: the CTA-pair GEMM on the four block
 # shapes (profiles/r02_gemm2_vs_cublas_ncu.txt: QKV 87, FF1 90, FF2 86, out-proj 60; FLOP-weighted over a block) and the fast attention
-# kernel (profiles/r02_attention_fast_ncu.txt: 41.6)
+# kernel (profiles/r02_attention_fast_ncu.txt: 41.6, captured on the 4-softmax-warp build; the final 8-warp build is ~4 % faster)
 NCU_TENSOR_PIPE_ACTIVE = {"gemm_bf16_tcgen05": (125 * 87 + 167 * 90 + 167 * 86 + 42 * 60) / 501.0, "joint_attention_tcgen05": 41.6}
 
 

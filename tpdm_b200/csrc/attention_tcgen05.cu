@@ -59,7 +59,7 @@ namespace {
 // row sum has passed 2^24 proposes a shift through shared memory and both apply it at the next checkpoint (see `tile` in the split branch).  16-column chunks
 // (two buffers of 16 registers).
 #ifndef TPDM_ATTN_SPLIT
-#define TPDM_ATTN_SPLIT 0
+#define TPDM_ATTN_SPLIT 1
 #endif
 constexpr int kAttnThreads = 256;
 constexpr bool kSplit = TPDM_ATTN_SPLIT != 0;

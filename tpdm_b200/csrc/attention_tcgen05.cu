@@ -6,7 +6,8 @@
 // [Bt][S][3*H*dp] through 4-D TMA tensor maps (no head permute, no concat copy); O is written token-major [Bt][S][H*dp]
 // so the output projection consumes it as-is.
 //
-// One CTA = one 128-row query tile of one (batch, head); 256 threads; two CTAs co-resident per SM (dp = 64).
+// One CTA = one 128-row query tile of one (batch, head); 256 threads (384 in the default fast kernel: warps 8-11 are four more softmax
+// warps on the same rows); two CTAs co-resident per SM (dp = 64).
 //   warp 0      TMA producer  (Q once, K/V tiles of 128 keys through a 2-stage smem ring)
 //   warp 1      MMA issuer for S = Q K^T: one 128 x 128 score tile per K tile (SS, dp/16 instructions of N = 128)
 //   warp 3      MMA issuer for O += P V (A = P from TMEM, B = V MN-major from smem, 8 instructions of N = dp)
@@ -38,7 +39,8 @@
 //    only when that exceeds m_used by more than 2^kRescaleThreshold does the row take the (rare, exact) path that moves the
 //    reference and rescales what was accumulated under the old one -- O, l and the P chunks of this tile already stored.
 // fp32 sums and bf16 P carry 8 exponent bits, so running up to 2^32 above the reference costs no precision, and the final 1/l cancels
-// the reference.  Round-2 measurements (B200, S = 4429, H = 24, Bt = 2): exact 320-327 us, fast 288-292 us (cuDNN SDPA: 283 us);
+// the reference.  Round-2 measurements (B200, S = 4429, H = 24, Bt = 2): exact 320-327 us, fast 288-292 us with four softmax warps per
+// CTA and 276 us with eight (TPDM_ATTN_SPLIT=1, the default: two threads per row, see the split branch of attn_cta); cuDNN SDPA: 283 us;
 // everything tried on the way is in profiles/r02_attention_experiments.txt.
 #include <cuda_bf16.h>
 

@@ -1,4 +1,6 @@
-"""Timeline of ONE attention CTA from the instrumented build (python -m tpdm_b200.build --variant trace TPDM_ATTN_TRACE):
+"""Timeline of ONE attention CTA from the instrumented build (python -m tpdm_b200.build --variant trace TPDM_ATTN_TRACE,TPDM_ATTN_SPLIT=0
+-- the per-tile stamps of the softmax warp live in the four-softmax-warp fast path and in the exact path (TPDM_ATTN_TRACE=2);
+the CTA-level stamps and the MMA-issuer stamps also work with the default eight-warp build):
 clock64() stamps of softmax warp 4 and of the two MMA-issuing warps, per 128-key tile.  Run on the GPU box:
     TPDM_B200_LIB=tpdm_b200/_build/libtpdm_trace.so python tools/attn_trace.py"""
 import ctypes as C
